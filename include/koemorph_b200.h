@@ -1,0 +1,172 @@
+/*
+ * koemorph_b200 -- C ABI of the B200 (sm_100a) audio -> ARKit-blendshape inference path.
+ *
+ * The reference (atsuki-ichikawa/KoeMorph) has no FFI / plugin / operator API for this path:
+ * its boundary is the PyTorch nn.Module surface.  These entry points are
+ * therefore what a binding for the path would bind; each one names the reference code it
+ * replaces (paths relative to the reference root).  The Python host side in
+ * koemorph_b200/ (a mirror of src/model and src/features) calls them through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host;
+ *   - every call is enqueued on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *   - the caller owns every buffer; kernels borrow them for the stream-ordered duration of the call;
+ *   - return value: 0 on success, a negative KOE_E_* code on misuse, a positive value is a cudaError_t;
+ *     koe_last_error() returns a human-readable message for the calling thread;
+ *   - there is no CPU fallback anywhere: without a CUDA device every call fails.
+ */
+#ifndef KOEMORPH_B200_H_
+#define KOEMORPH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KOE_OK 0
+#define KOE_E_INVALID (-1)   /* bad argument (null pointer, size out of range, misaligned) */
+#define KOE_E_UNSUPPORTED (-2) /* configuration outside what the kernels implement */
+#define KOE_E_NODEVICE (-3)
+
+#define KOE_N_MELS 80
+#define KOE_N_FFT 1024
+#define KOE_N_BLENDSHAPES 52
+#define KOE_N_MOUTH 28
+#define KOE_N_EXPR 24
+#define KOE_D_MODEL 256
+#define KOE_N_HEADS 8
+#define KOE_NO_EDGE (-1000000) /* lo_rel_hops / hi_rel_hops: no window edge on that side */
+#define KOE_MAX_EDGE 2         /* ceil((n_fft/2) / hop) for hop >= 256 */
+
+const char* koe_last_error(void);
+int koe_version(void);
+/* number of kernels launched by this library in this process since load / since the last reset */
+int64_t koe_launch_count(void);
+void koe_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Log-mel frontend.
+ * Replaces: SimplifiedDualStreamModel.extract_mel_features, src/model/simplified_dual_stream_model.py:166-229
+ * (librosa.feature.melspectrogram(n_fft=1024, hop, n_mels=80, fmin, fmax) + power_to_db(ref=max) + (x+80)/80)
+ * and the librosa calls of MelSlidingWindowExtractor, src/features/mel_sliding_window.py:224-230,280-295.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct koe_frontend koe_frontend_t; /* opaque: Hann window, FFT twiddles, sparse Slaney filterbank on one device */
+
+int koe_frontend_create(int device, int sample_rate, int n_fft, int n_mels, float fmin, float fmax,
+                        koe_frontend_t** out);
+int koe_frontend_destroy(koe_frontend_t* fe);
+/* copy the dense (n_mels x (1+n_fft/2)) float32 filterbank to host memory (for parity tests) */
+int koe_frontend_filterbank_host(const koe_frontend_t* fe, float* fb_host);
+
+/*
+ * Mel *power* of n_frames frames of every clip.  Output row j is frame g = frame_offset + j*frame_step:
+ * the 1024-sample periodic-Hann frame centred on sample g*hop (librosa center=True).  Samples outside
+ * [0, n_samples) read as zero (librosa pad_mode="constant"); in addition, when lo_rel_hops != KOE_NO_EDGE
+ * samples before (g + lo_rel_hops)*hop read as zero, and when hi_rel_hops != KOE_NO_EDGE samples at or
+ * after (g + hi_rel_hops)*hop read as zero.  The edge variants are the first / last frames of the sliding
+ * windows of SequentialDualStreamModel.forward (src/model/sequential_dual_stream_model.py:101-120):
+ * a window starting at frame i sees frame i with lo_rel_hops=0 and frame i+W with hi_rel_hops=0.
+ *   audio      [n_clips][audio_stride] float32
+ *   power      [n_clips][n_frames][80] float32   (sum_k fb[m][k] * |X_g[k]|^2)
+ *   frame_max  [n_clips][n_frames]     float32   (max_m power[.,j,m]); may be NULL
+ */
+int koe_logmel_power(const koe_frontend_t* fe, const float* audio, int64_t audio_stride, int n_clips,
+                     int n_samples, int hop, int n_frames, int frame_offset, int frame_step, int lo_rel_hops,
+                     int hi_rel_hops, float* power, float* frame_max, void* stream);
+
+/*
+ * power_to_db(ref = max over the clip's n_frames frames, amin=1e-10, top_db=80) followed by (x+80)/80.
+ * Writes the long-term features [n_clips][n_frames][80] and the short-term detail = last three frames
+ * [n_clips][3][80] (zero rows when n_frames < 3: simplified_dual_stream_model.py:206-212).
+ * db_only != 0 skips the (x+80)/80 rescale (MelSlidingWindowExtractor semantics, mel_sliding_window.py:295).
+ */
+int koe_logmel_normalise(const float* power, const float* frame_max, int n_clips, int n_frames, int db_only,
+                         float* long_term, float* short_term, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dual-stream attention core.
+ * Replaces: DualStreamCrossAttention.forward, src/model/dual_stream_attention.py:162-280, and the
+ * 264 -> 256 compression of OpenSMILEeGeMAPSExtractor.get_concatenated_features,
+ * src/features/opensmile_extractor.py:583-604.
+ * The host folds batch-invariant products once per weight update (koemorph_b200/model/folding.py);
+ * all matrices below are row-major float32 and stored TRANSPOSED ([in][out]) for coalesced streaming.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t k_mel;     /* mel_sequence_length + 3: 259 (30 fps) or 515 (60 fps) */
+  int32_t k_mel_pad; /* rows allocated in wc_t, multiple of 16, zero filled */
+  int32_t emo_in;    /* 264 (compression folded in) or 256 (DualStreamCrossAttention standalone) */
+  int32_t emo_in_pad;
+  float b2;          /* blendshape_decoder.3.bias */
+  float ln_eps;      /* 1e-5 */
+  const float* wc_t;   /* [k_mel_pad][256]  mel_channel_encoder.weight^T                         (:211) */
+  const float* bc;     /* [256] */
+  const float* ln_g;   /* [256] mel_norm.weight                                                  (:212) */
+  const float* ln_b;   /* [256] */
+  const float* qk_t;   /* [256][256]: column h*28+q = ((Wq q_q + bq)_h / sqrt(32)) Wk_h; cols 224..255 zero (:225-230) */
+  const float* wv_t;   /* [256][256] mel_attention.in_proj_weight[512:768]^T */
+  const float* bv;     /* [256] */
+  const float* wa_t;   /* [256][128] (decoder.0 . mel_output_proj . out_proj)^T                  (:231,248) */
+  const float* ba;     /* [128] */
+  const float* w2;     /* [128] blendshape_decoder.3.weight */
+  const float* coef;   /* [52] 0.5*(softmax(mel_weights/T) + softmax(emotion_weights/T))         (:252-267) */
+  const int32_t* mouth_idx; /* [28] */
+  const int32_t* expr_idx;  /* [24] */
+  const float* we1_t;  /* [emo_in_pad][256] (emotion_encoder . compression)^T                    (:216) */
+  const float* be1;    /* [256] */
+  const float* eln_g;  /* [256] emotion_norm */
+  const float* eln_b;  /* [256] */
+  const float* we2_t;  /* [256][128] (decoder.0 . emotion_output_proj . out_proj_e . Wv_e)^T     (:234-240,248) */
+  const float* be2;    /* [128] */
+} koe_core_weights;
+
+/*
+ * Emotion stream: one key per clip, so softmax == 1 and all 24 expression queries give the same value
+ * (dual_stream_attention.py:234-240).  emo_in [n_clips][w->emo_in] -> expr_sigmoid [n_clips].
+ */
+int koe_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid,
+                       void* stream);
+
+/*
+ * Windows of mel power -> blendshape frames.  Output frame i of clip b uses the window whose first frame
+ * is g0 = i*stride_frames and that holds frames_per_window (T) frames; its frame k comes from
+ *   power[1 + 2*k]       row (b, i)        lo-edge variant k      if k <  n_edge
+ *   power[2 + 2*(T-1-k)] row (b, i)        hi-edge variant T-1-k  if k >= T - n_edge
+ *   power[0]             row (b, g0 + k)   plain frames           otherwise.
+ * i.e. power[0] is [n_clips][n_frames][80] over the clip's global frames, and every edge buffer is
+ * [n_clips][n_out][80], one row per window (koe_logmel_power with frame_offset/frame_step = the window grid).
+ * dB reference = max over the window's frames (librosa ref=np.max), -80 dB clamp, (x+80)/80,
+ * long-term = first min(T, mel_seq) frames (zero padded to mel_seq), short-term = last 3 frames.
+ *   frame_max[j]  same leading shape as power[j] without the 80
+ *   expr_sigmoid  [n_clips] from koe_emotion_stream
+ *   out           [n_clips][n_out][52]  final blendshapes (before temporal smoothing)
+ *   sigmoid_out   [n_clips][n_out][52]  decoder output before the stream-weight fusion, or NULL
+ *   attn_out      [n_clips][n_out][28][80] head-averaged mel attention weights, or NULL
+ * precision: 0 = fp32 CUDA-core FMA; 1 = tf32 tcgen05; 2 = bf16 tcgen05.
+ */
+int koe_dual_stream_windows(const koe_core_weights* w, const float* const* power, const float* const* frame_max,
+                            int n_edge, int n_clips, int n_frames, int n_out, int stride_frames,
+                            int frames_per_window, const float* expr_sigmoid, float* out, float* sigmoid_out,
+                            float* attn_out, int precision, void* stream);
+
+/*
+ * Same core on already-normalised features: the DualStreamCrossAttention.forward signature
+ * (dual_stream_attention.py:162-168).  mel_long [n_clips][n_long][80] (zero padded / truncated to mel_seq),
+ * mel_short [n_clips][3][80]; outputs as above with n_out = 1.
+ */
+int koe_dual_stream_features(const koe_core_weights* w, const float* mel_long, int n_long, const float* mel_short,
+                             int n_clips, const float* expr_sigmoid, float* out, float* sigmoid_out,
+                             float* attn_out, int precision, void* stream);
+
+/*
+ * Learnable-alpha exponential smoothing along the frame axis, in place
+ * (apply_temporal_smoothing, src/model/simplified_dual_stream_model.py:341-368):
+ *   y_0 = x_0 (or alpha*x_0 + (1-alpha)*state when state != NULL and has_state != 0); y_t = alpha*x_t + (1-alpha)*y_{t-1}.
+ * frames [n_clips][n_out][52]; state [n_clips][52] receives y_{n_out-1} when non-NULL.
+ */
+int koe_ema_scan(float* frames, int n_clips, int n_out, float alpha, float* state, int has_state, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOEMORPH_B200_H_ */

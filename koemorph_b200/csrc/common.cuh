@@ -1,0 +1,80 @@
+// Shared helpers for the koemorph_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/koemorph_b200.h"
+
+namespace koe {
+
+// ---- error plumbing for the C ABI ---------------------------------------------------------------
+inline char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+inline std::atomic<int64_t>& launch_counter() {
+  static std::atomic<int64_t> c{0};
+  return c;
+}
+inline void count_launch(int n = 1) { launch_counter().fetch_add(n, std::memory_order_relaxed); }
+
+#define KOE_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return koe::fail((int)_e, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                                 \
+  } while (0)
+
+#define KOE_REQUIRE(cond, ...)                                   \
+  do {                                                           \
+    if (!(cond)) return koe::fail(KOE_E_INVALID, __VA_ARGS__);   \
+  } while (0)
+
+// ---- device helpers ----------------------------------------------------------------------------
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+// librosa.power_to_db constants (amin = 1e-10, top_db = 80) -- see oracle/koemorph_oracle.py::power_to_db
+constexpr float kAmin = 1e-10f;
+constexpr float kTopDb = 80.0f;
+
+__device__ __forceinline__ float power_db(float p) { return 10.0f * log10f(fmaxf(p, kAmin)); }
+// dB relative to ref_db, clamped at -top_db, optionally rescaled to [0, 1] by (x + 80) / 80
+__device__ __forceinline__ float normalise_db(float p, float ref_db, bool rescale) {
+  float x = fmaxf(power_db(p) - ref_db, -kTopDb);
+  return rescale ? (x + 80.0f) / 80.0f : x;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+}  // namespace koe

@@ -1,0 +1,90 @@
+"""Device log-mel frontend: thin host wrapper over koe_frontend_* / koe_logmel_* (include/koemorph_b200.h).
+
+Replaces the per-clip librosa loop of the reference
+(src/model/simplified_dual_stream_model.py:184-229: melspectrogram(n_fft=1024, hop, n_mels=80,
+fmin=80, fmax=8000) -> power_to_db(ref=np.max) -> (x + 80) / 80).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+N_FFT = 1024
+N_MELS = 80
+
+
+class LogMelFrontend:
+    """One handle (Hann window, FFT twiddles, sparse Slaney filterbank) per CUDA device."""
+
+    _cache: Dict[Tuple, "LogMelFrontend"] = {}
+
+    def __init__(self, device, sample_rate: int = 16000, n_fft: int = N_FFT, n_mels: int = N_MELS,
+                 f_min: float = 80.0, f_max: float = 8000.0):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError(f"LogMelFrontend needs a CUDA device, got {device}; there is no CPU path")
+        self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        self.sample_rate, self.n_fft, self.n_mels, self.f_min, self.f_max = sample_rate, n_fft, n_mels, f_min, f_max
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.koe_frontend_create(self.device.index, sample_rate, n_fft, n_mels, float(f_min),
+                                                 float(f_max), C.byref(h)), "koe_frontend_create")
+        self._h = h
+
+    @classmethod
+    def get(cls, device, sample_rate=16000, n_fft=N_FFT, n_mels=N_MELS, f_min=80.0, f_max=8000.0):
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, sample_rate, n_fft, n_mels, float(f_min), float(f_max))
+        if key not in cls._cache:
+            cls._cache[key] = cls(torch.device("cuda", idx), sample_rate, n_fft, n_mels, f_min, f_max)
+        return cls._cache[key]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.koe_frontend_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def filterbank(self) -> np.ndarray:
+        fb = np.empty((self.n_mels, 1 + self.n_fft // 2), np.float32)
+        _lib.check(self._lib.koe_frontend_filterbank_host(self._h, fb.ctypes.data_as(C.c_void_p)))
+        return fb
+
+    def power(self, audio: torch.Tensor, hop: int, n_frames: int, frame_offset: int = 0, frame_step: int = 1,
+              lo_rel: Optional[int] = None, hi_rel: Optional[int] = None,
+              out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """audio (B, L) float32 CUDA -> mel power (B, n_frames, 80), per-frame max (B, n_frames)."""
+        audio = _lib.require_cuda(audio, "audio")
+        if audio.dim() != 2:
+            raise ValueError(f"audio must be (B, L), got {tuple(audio.shape)}")
+        B, L = audio.shape
+        if out is None:
+            power = torch.empty((B, n_frames, self.n_mels), dtype=torch.float32, device=audio.device)
+            fmax = torch.empty((B, n_frames), dtype=torch.float32, device=audio.device)
+        else:
+            power, fmax = out
+        with torch.cuda.device(audio.device):
+            _lib.check(self._lib.koe_logmel_power(
+                self._h, audio.data_ptr(), audio.stride(0), B, L, hop, n_frames, frame_offset, frame_step,
+                _lib.KOE_NO_EDGE if lo_rel is None else lo_rel, _lib.KOE_NO_EDGE if hi_rel is None else hi_rel,
+                power.data_ptr(), fmax.data_ptr(), _lib.stream_ptr(audio.device)), "koe_logmel_power")
+        return power, fmax
+
+    def normalise(self, power: torch.Tensor, fmax: torch.Tensor, db_only: bool = False):
+        """power_to_db(ref=clip max, top_db=80) [+ (x+80)/80] -> long-term (B, T, 80), short-term (B, 3, 80)."""
+        B, T, M = power.shape
+        long_term = torch.empty_like(power)
+        short_term = torch.empty((B, 3, M), dtype=torch.float32, device=power.device)
+        with torch.cuda.device(power.device):
+            _lib.check(self._lib.koe_logmel_normalise(power.data_ptr(), fmax.data_ptr(), B, T, int(db_only),
+                                                      long_term.data_ptr(), short_term.data_ptr(),
+                                                      _lib.stream_ptr(power.device)), "koe_logmel_normalise")
+        return long_term, short_term

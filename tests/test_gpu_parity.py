@@ -1,0 +1,226 @@
+"""GPU parity tests (-m gpu): the CUDA path, reached through the C ABI, against the CPU oracle and the
+golden vectors of the unmodified reference.
+
+Tolerances (BASELINE.md section 5 / north_star):
+  * log-mel, normalised (dB + 80) / 80:   |d| <= 1e-4 * |ref| + 2e-5   (1e-4 relative; the absolute floor
+    covers values on the -80 dB clamp where "relative" is undefined)
+  * blendshapes, fp32 path:               |d| <= 1e-3 absolute (north_star) -- and, because random-init outputs are
+    ~0.01, the tighter gates we add: <= 2e-6 on the output, <= 2e-5 on the pre-fusion sigmoid, <= 2e-5 on the
+    head-averaged attention weights.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import koemorph_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGMEL_RTOL, LOGMEL_ATOL = 1e-4, 2e-5
+OUT_ATOL, SIG_ATOL, ATTN_ATOL = 2e-6, 2e-5, 2e-5
+
+
+@pytest.fixture(scope="module")
+def K():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import koemorph_b200
+    from koemorph_b200 import _lib
+    _lib.load()  # fails loudly if the CUDA library is missing
+    return koemorph_b200
+
+
+def _model(K, spec, sequential):
+    w = O.make_weights(spec["wseed"], spec["fps"], style=spec["style"])
+    kw = dict(target_fps=spec["fps"], mel_sequence_length=256 if spec["fps"] == 30 else 512)
+    m = (K.SequentialDualStreamModel(stride_frames=spec.get("stride", 1), **kw) if sequential
+         else K.SimplifiedDualStreamModel(**kw))
+    m.load_state_dict(O.model_state_dict(w), strict=True)
+    m.set_compression_layer(torch.from_numpy(w["compression.weight"]), torch.from_numpy(w["compression.bias"]))
+    return m.cuda().eval(), w
+
+
+def _inputs(spec):
+    audio, eg = O.make_inputs(spec["iseed"], spec["B"], spec["L"], spec["kind"])
+    return torch.from_numpy(audio).cuda(), torch.from_numpy(eg).cuda()
+
+
+def _close(got, ref, rtol, atol, what):
+    got = got.detach().cpu().double().numpy() if torch.is_tensor(got) else np.asarray(got, np.float64)
+    ref = ref.detach().cpu().double().numpy() if torch.is_tensor(ref) else np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    err = np.abs(got - ref) - (atol + rtol * np.abs(ref))
+    assert err.max() <= 0, f"{what}: max |d| = {np.abs(got - ref).max():.3e} (excess {err.max():.3e})"
+
+
+SINGLE = ["single_noise_init", "single_speech_stress", "single_burst_stress", "single_sine_stress",
+          "single_step_stress", "single_silence_init", "single_short_clip", "single_long_clip", "single_60fps"]
+SEQ = ["seq_clip_T1", "seq_13_frames", "seq_20s", "seq_stride3", "seq_60fps", "seq_burst_edge"]
+
+
+def test_filterbank_matches_oracle(K):
+    from koemorph_b200.features.mel_frontend import LogMelFrontend
+    fb = LogMelFrontend.get("cuda").filterbank()
+    ref = O.mel_filterbank()
+    assert np.abs(fb - ref).max() <= 1.2e-7 * ref.max()
+    assert ((fb > 0) == (ref > 0)).all()
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_logmel_vs_golden(K, golden, name):
+    cases, data = golden
+    spec = cases[name]
+    m, _ = _model(K, spec, False)
+    audio, _ = _inputs(spec)
+    lt, st = m.extract_mel_features(audio)
+    _close(lt, data[f"{name}/logmel"], LOGMEL_RTOL, LOGMEL_ATOL, "long-term log-mel")
+    _close(st, data[f"{name}/logmel_short"], LOGMEL_RTOL, LOGMEL_ATOL, "short-term log-mel")
+
+
+@pytest.mark.parametrize("kind", ["noise", "speechlike", "level_step", "sine", "silence_burst"])
+def test_mel_power_vs_float64_oracle(K, kind):
+    """Mel power itself (before the log) against the float64 restatement, relative to each clip's peak."""
+    from koemorph_b200.features.mel_frontend import LogMelFrontend
+    audio, _ = O.make_inputs(31, 3, 136000, kind)
+    fe = LogMelFrontend.get("cuda")
+    power, fmax = fe.power(torch.from_numpy(audio).cuda(), 533, 256)
+    power = power.cpu().double().numpy()
+    for b in range(3):
+        ref = O.melspectrogram(audio[b], hop_length=533, exact=True).T
+        assert np.abs(power[b] - ref).max() <= 2e-6 * ref.max()
+        # relative accuracy wherever the band is within 60 dB of the clip peak
+        big = ref > 1e-6 * ref.max()
+        assert (np.abs(power[b] - ref)[big] / ref[big]).max() < 2e-4
+        np.testing.assert_allclose(fmax[b].cpu().numpy(), power[b].max(axis=1), rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_forward_single_vs_golden(K, golden, name):
+    cases, data = golden
+    spec = cases[name]
+    m, _ = _model(K, spec, False)
+    audio, eg = _inputs(spec)
+    out = m(audio, return_attention=True, egemaps=eg)
+    _close(out["blendshapes"], data[f"{name}/blendshapes"], 0, OUT_ATOL, "blendshapes")
+    _close(out["mel_blendshapes"], data[f"{name}/mel_blendshapes"], 0, SIG_ATOL, "mel_blendshapes")
+    _close(out["emotion_blendshapes"], data[f"{name}/emotion_blendshapes"], 0, SIG_ATOL, "emotion_blendshapes")
+    _close(out["mel_attention_weights"], data[f"{name}/mel_attention_weights"], 0, ATTN_ATOL, "mel attention")
+    assert out["emotion_attention_weights"].shape == (spec["B"], 24, 1)
+    assert bool((out["emotion_attention_weights"] == 1).all())
+    # without return_attention only the blendshapes come back, and they are identical
+    m.reset_temporal_state()
+    out2 = m(audio, egemaps=eg)
+    assert set(out2) == {"blendshapes"} and torch.equal(out2["blendshapes"], out["blendshapes"])
+
+
+@pytest.mark.parametrize("name", SEQ)
+def test_forward_sequence_vs_golden(K, golden, name):
+    cases, data = golden
+    spec = cases[name]
+    m, _ = _model(K, spec, True)
+    audio, eg = _inputs(spec)
+    out = m(audio, return_attention=True, egemaps=eg)
+    ref = data[f"{name}/blendshapes"]
+    assert out["num_frames"] == ref.shape[1] and out["fps"] == spec["fps"]
+    _close(out["blendshapes"], ref, 0, OUT_ATOL, "sequence blendshapes")
+    n = data[f"{name}/mel_attention_weights"].shape[1]
+    _close(out["mel_attention_weights"][:, :n], data[f"{name}/mel_attention_weights"], 0, ATTN_ATOL, "mel attention")
+    assert out["emotion_attention_weights"].shape == (spec["B"], ref.shape[1], 24, 1)
+
+
+def test_core_standalone_vs_oracle(K):
+    """DualStreamCrossAttention.forward on ready-made features, T shorter / equal / longer than 256."""
+    w = O.make_weights(21, 30, style="stress")
+    core = K.DualStreamCrossAttention().cuda().eval()
+    core.load_state_dict({k[len("dual_stream_attention."):]: v for k, v in O.model_state_dict(w).items()
+                          if k.startswith("dual_stream_attention.")})
+    rng = np.random.default_rng(5)
+    for T in (100, 256, 300):
+        lt = rng.uniform(0, 1, (4, T, 80)).astype(np.float32)
+        st = rng.uniform(0, 1, (4, 3, 80)).astype(np.float32)
+        emo = rng.standard_normal((4, 256)).astype(np.float32)
+        ref = O.dual_stream_core(w, lt, st, emo, return_attention=True)
+        out = core(torch.from_numpy(lt).cuda(), torch.from_numpy(st).cuda(), torch.from_numpy(emo).cuda(),
+                   return_attention=True)
+        _close(out["blendshapes"], ref["blendshapes"], 0, OUT_ATOL, f"core T={T}")
+        _close(out["mel_attention_weights"], ref["mel_attention_weights"], 0, ATTN_ATOL, f"attn T={T}")
+        _close(out["mel_blendshapes"], ref["mel_blendshapes"], 0, SIG_ATOL, f"sigmoid T={T}")
+
+
+@pytest.mark.parametrize("T", [1, 2, 31, 32, 33, 345, 1000])
+def test_ema_scan_vs_oracle(K, T):
+    from koemorph_b200 import _lib
+    x = torch.rand(5, T, 52, dtype=torch.float32)
+    alpha = 0.6899744811276125
+    ref = O.ema_smooth(x.double(), alpha)
+    y = x.cuda().clone()
+    state = torch.zeros(5, 52, device="cuda")
+    _lib.check(_lib.load().koe_ema_scan(y.data_ptr(), 5, T, alpha, state.data_ptr(), 0, _lib.stream_ptr()))
+    _close(y, ref, 1e-6, 1e-7, "ema scan")
+    _close(state, ref[:, -1], 1e-6, 1e-7, "ema state")
+    # continuing from a state == one long scan
+    y2 = x.cuda().clone()
+    cut = max(1, T // 3)
+    st = torch.zeros(5, 52, device="cuda")
+    a, b = y2[:, :cut].contiguous(), y2[:, cut:].contiguous()
+    _lib.check(_lib.load().koe_ema_scan(a.data_ptr(), 5, cut, alpha, st.data_ptr(), 0, _lib.stream_ptr()))
+    if T - cut > 0:
+        _lib.check(_lib.load().koe_ema_scan(b.data_ptr(), 5, T - cut, alpha, st.data_ptr(), 1, _lib.stream_ptr()))
+    _close(torch.cat([a, b], 1), ref, 1e-6, 1e-7, "ema scan with carried state")
+
+
+def test_stateful_smoothing_across_calls(K, golden):
+    """SimplifiedDualStreamModel keeps an EMA across forward calls (reference :341-368)."""
+    cases, _ = golden
+    spec = cases["single_speech_stress"]
+    m, w = _model(K, spec, False)
+    audio, eg = _inputs(spec)
+    a2, e2 = O.make_inputs(999, spec["B"], spec["L"], "noise")
+    r1 = O.forward_single(w, audio.cpu().numpy(), eg.cpu().numpy())["blendshapes"]
+    r2 = O.forward_single(w, a2, e2)["blendshapes"]
+    alpha = O.smoothing_alpha(w)
+    o1 = m(audio, egemaps=eg)["blendshapes"]
+    o2 = m(torch.from_numpy(a2).cuda(), egemaps=torch.from_numpy(e2).cuda())["blendshapes"]
+    _close(o1, r1, 0, OUT_ATOL, "first call passes through")
+    _close(o2, alpha * r2 + (1 - alpha) * r1, 0, OUT_ATOL, "second call is smoothed")
+    m.reset_temporal_state()
+    _close(m(torch.from_numpy(a2).cuda(), egemaps=torch.from_numpy(e2).cuda())["blendshapes"], r2, 0, OUT_ATOL,
+           "reset")
+
+
+def test_full_size_properties(K):
+    """BASELINE config 1 size (512 clips x 8.5 s): properties that need no oracle run.
+
+    * clips are independent: a clip's output does not depend on its batch neighbours or position;
+    * the dB reference is the clip's own max, so scaling a clip by 2^k changes nothing (exact in fp32);
+    * a small batch cut out of the big one is checked against the oracle."""
+    spec = dict(wseed=1235, style="stress", fps=30)
+    m, w = _model(K, spec, True)
+    B = 512
+    g = torch.Generator(device="cuda").manual_seed(7)
+    audio = 0.1 * torch.randn(B, 136000, device="cuda", generator=g)
+    eg = torch.randn(B, 264, device="cuda", generator=g)
+    out = m(audio, egemaps=eg)["blendshapes"]
+    assert out.shape == (B, 1, 52) and bool(torch.isfinite(out).all()) and float(out.min()) >= 0 and float(out.max()) <= 1
+    perm = torch.randperm(B, device="cuda", generator=g)
+    out_p = m(audio[perm].contiguous(), egemaps=eg[perm].contiguous())["blendshapes"]
+    assert torch.equal(out_p, out[perm])
+    out_s = m((audio * 4.0).contiguous(), egemaps=eg)["blendshapes"]
+    assert torch.equal(out_s, out)
+    sub = [0, 17, 255, 511]
+    ref = O.forward_sequence(w, audio[sub].cpu().numpy(), eg[sub].cpu().numpy())["blendshapes"]
+    _close(out[sub], ref, 0, OUT_ATOL, "full-size batch vs oracle")
+
+
+def test_argument_validation(K):
+    m = K.SequentialDualStreamModel().cuda()
+    a = torch.zeros(2, 136000, device="cuda")
+    with pytest.raises(RuntimeError, match="egemaps is required"):
+        m(a)
+    with pytest.raises(TypeError):
+        m(a.double(), egemaps=torch.zeros(2, 264, device="cuda"))
+    with pytest.raises(ValueError):
+        m(a, egemaps=torch.zeros(3, 264, device="cuda"))
+    with pytest.raises(ValueError):
+        m(torch.zeros(136000, device="cuda"), egemaps=torch.zeros(1, 264, device="cuda"))
+    out = m(a, egemaps=torch.zeros(2, 3, 88, device="cuda"))
+    assert out["blendshapes"].shape == (2, 1, 52)
