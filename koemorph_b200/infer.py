@@ -1,0 +1,61 @@
+"""Host-buffer entry point: pinned host audio in, host blendshapes out, copies overlapped with compute.
+
+This is the call an application makes when its audio lives in host memory (the reference's own calling
+convention is host numpy -> per-clip librosa, src/model/simplified_dual_stream_model.py:184-229).
+Clips are independent, so the batch is cut into chunks that flow through a two-stage pipeline on two CUDA
+streams: while chunk i runs the kernels, chunk i+1 is crossing PCIe.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+class HostPipeline:
+    def __init__(self, model, chunk_clips: int = 64):
+        self.model = model
+        self.chunk = int(chunk_clips)
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("HostPipeline needs the model on a CUDA device")
+        self._streams = [torch.cuda.Stream(self.device) for _ in range(2)]
+        self._bufs = {}
+
+    def _buffers(self, slot: int, n: int, L: int):
+        key = (slot, L)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.empty(self.chunk, L, dtype=torch.float32, device=self.device),
+                               torch.empty(self.chunk, 264, dtype=torch.float32, device=self.device))
+        a, e = self._bufs[key]
+        return a[:n], e[:n]
+
+    @torch.no_grad()
+    def __call__(self, audio_host: torch.Tensor, egemaps_host: torch.Tensor,
+                 out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """audio_host (B, L) float32 and egemaps_host (B, 264) in (ideally pinned) host memory ->
+        (B, T_out, 52) host tensor.  Synchronises before returning."""
+        if audio_host.is_cuda or egemaps_host.is_cuda:
+            raise ValueError("HostPipeline takes host tensors; call the model directly for device tensors")
+        B, L = audio_host.shape
+        eg = egemaps_host.reshape(B, 264)
+        n_out = self.model.num_output_frames(L) if hasattr(self.model, "num_output_frames") else None
+        shape = (B, n_out, 52) if n_out is not None else (B, 52)
+        if out_host is None:
+            out_host = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        cur = torch.cuda.current_stream(self.device)
+        for s in self._streams:
+            s.wait_stream(cur)
+        for ci, c0 in enumerate(range(0, B, self.chunk)):
+            n = min(self.chunk, B - c0)
+            s = self._streams[ci & 1]
+            a_dev, e_dev = self._buffers(ci & 1, n, L)
+            with torch.cuda.stream(s):
+                a_dev.copy_(audio_host[c0:c0 + n], non_blocking=True)
+                e_dev.copy_(eg[c0:c0 + n], non_blocking=True)
+                res = self.model(a_dev, egemaps=e_dev)["blendshapes"]
+                out_host[c0:c0 + n].copy_(res, non_blocking=True)
+        for s in self._streams:
+            cur.wait_stream(s)
+        cur.synchronize()
+        return out_host

@@ -191,7 +191,8 @@ def test_full_size_properties(K):
     """BASELINE config 1 size (512 clips x 8.5 s): properties that need no oracle run.
 
     * clips are independent: a clip's output does not depend on its batch neighbours or position;
-    * the dB reference is the clip's own max, so scaling a clip by 2^k changes nothing (exact in fp32);
+    * the dB reference is the clip's own max, so scaling a clip by 2^k changes nothing up to the rounding of
+      log10f(16 p) - log10f(16 ref) versus log10f(p) - log10f(ref);
     * a small batch cut out of the big one is checked against the oracle."""
     spec = dict(wseed=1235, style="stress", fps=30)
     m, w = _model(K, spec, True)
@@ -205,7 +206,7 @@ def test_full_size_properties(K):
     out_p = m(audio[perm].contiguous(), egemaps=eg[perm].contiguous())["blendshapes"]
     assert torch.equal(out_p, out[perm])
     out_s = m((audio * 4.0).contiguous(), egemaps=eg)["blendshapes"]
-    assert torch.equal(out_s, out)
+    _close(out_s, out, 0, 5e-7, "scale invariance")
     sub = [0, 17, 255, 511]
     ref = O.forward_sequence(w, audio[sub].cpu().numpy(), eg[sub].cpu().numpy())["blendshapes"]
     _close(out[sub], ref, 0, OUT_ATOL, "full-size batch vs oracle")
