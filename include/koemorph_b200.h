@@ -118,6 +118,11 @@ typedef struct {
   const float* eln_b;  /* [256] */
   const float* we2_t;  /* [256][128] (decoder.0 . emotion_output_proj . out_proj_e . Wv_e)^T     (:234-240,248) */
   const float* be2;    /* [128] */
+  /* tcgen05 path (precision 2): the bf16 weight matrices pre-tiled into the UMMA no-swizzle K-major core-matrix
+   * layout, as 16 KiB pipeline-stage images in consumption order (see csrc/dual_stream_tc.cu); NULL if absent */
+  const void* tc_bf16;
+  int32_t tc_stages;   /* number of 16 KiB stage images behind tc_bf16 */
+  int32_t reserved_;
 } koe_core_weights;
 
 /*

@@ -30,6 +30,7 @@ class CoreWeightsStruct(C.Structure):
         ("mouth_idx", C.c_void_p), ("expr_idx", C.c_void_p),
         ("we1_t", C.c_void_p), ("be1", C.c_void_p), ("eln_g", C.c_void_p), ("eln_b", C.c_void_p),
         ("we2_t", C.c_void_p), ("be2", C.c_void_p),
+        ("tc_bf16", C.c_void_p), ("tc_stages", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

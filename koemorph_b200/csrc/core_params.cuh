@@ -1,0 +1,33 @@
+// Launch parameters shared by the CUDA-core and the tcgen05 implementations of the dual-stream core.
+#pragma once
+#include "common.cuh"
+
+namespace koe {
+
+struct CoreParams {
+  koe_core_weights w;
+  const float* power[1 + 2 * KOE_MAX_EDGE];
+  const float* fmax[1 + 2 * KOE_MAX_EDGE];
+  int n_edge, n_clips, n_frames, n_out, stride_frames, frames_per_window, mel_seq;
+  const float* expr_sigmoid;
+  float* out;
+  float* sigmoid_out;
+  float* attn_out;
+  // prenormalised mode (koe_dual_stream_features): rows come from mel_long / mel_short as they are
+  const float* mel_long;
+  const float* mel_short;
+  int n_long;
+};
+
+// frame k of window wi of clip b: which buffer and which row (see koe_dual_stream_windows in the header)
+__device__ __forceinline__ int window_variant(const CoreParams& p, int k) {
+  if (k < p.n_edge) return 1 + 2 * k;
+  if (k >= p.frames_per_window - p.n_edge) return 2 + 2 * (p.frames_per_window - 1 - k);
+  return 0;
+}
+__device__ __forceinline__ long long window_row(const CoreParams& p, int variant, int b, int wi, int k) {
+  return variant == 0 ? (long long)b * p.n_frames + (long long)wi * p.stride_frames + k
+                      : (long long)b * p.n_out + wi;
+}
+
+}  // namespace koe

@@ -1,11 +1,535 @@
-// tcgen05 / TMEM implementation of the dual-stream core (precision 1 = tf32, 2 = bf16).
+// tcgen05 / TMEM implementation of the dual-stream core (precision 2: bf16 operands, fp32 accumulation).
+//
+// Same arithmetic as dual_stream_fp32_kernel (reference src/model/dual_stream_attention.py:162-280) with
+// every GEMM on the 5th-generation tensor cores:
+//
+//   phase  MMA (M=128, cta_group::1, kind::f16)                         accumulator (TMEM columns)
+//   G1     z[tok 128(80) x 256]   = Xn[tok x 272] . Wc[256 x 272]^T      [0,256)
+//   S      s[hq 128 x tok 80]     = Qk_t[128 x 256] . enc[80 x 256]^T    [256,336) [336,416)   2 tiles of 4 heads
+//   VT     vT[d 128 x tok 80]     = Wv_t[128 x 256] . enc[80 x 256]^T    [0,80) [80,160)       2 tiles
+//   PV     o[hq 128 x d 128]      = P_t[128 x 80] . vT_t[128 x 80]^T     [160,288) [288,416)   (diagonal 32x32 blocks used)
+//   H1     h[q 128(28) x 128]     = O[q x 256] . Wa[128 x 256]^T         [0,128)
+//
+// Operands live in shared memory in the canonical UMMA *no-swizzle K-major* layout: 8-row x 16-byte core
+// matrices, element (r, k) at (r/8)*SBO + (k/8)*128 + (r%8)*16 + (k%8)*2 bytes.  Activations are written in that
+// layout by the epilogue threads; weights are pre-tiled on the host into the same layout, 16 KiB per pipeline
+// stage, so the producer moves one stage with a single cp.async.bulk (TMA bulk copy) that completes on an
+// mbarrier.  Roles: warps 0-3 = SIMT (operand staging, TMEM epilogues; thread t owns TMEM lane t), warp 4 = TMA
+// producer, warp 5 = TMEM allocator + single-thread MMA issuer.  Phases are serialised by two mbarriers
+// (mma_go: 128 SIMT arrivals; mma_done: tcgen05.commit); the weight ring runs ahead across phases and windows.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+#include "core_params.cuh"
 
 namespace koe {
-struct CoreParams;
-int launch_dual_stream_tc(const CoreParams& p, int precision, cudaStream_t stream) {
-  (void)p;
-  (void)stream;
-  return fail(KOE_E_UNSUPPORTED, "koe_dual_stream_windows: precision %d (tensor-core path) is not built yet", precision);
+
+namespace tc {
+
+constexpr int kThreads = 192;
+constexpr int kSimt = 128;
+constexpr int kStageBytes = 16384;
+constexpr int kRing = 4;
+constexpr int kTok = 80;
+constexpr int kKMel = 259;        // 30 fps only (mel_sequence_length 256 + 3)
+constexpr int kKMelPad = 272;     // multiple of 16
+constexpr int kA1Chunks = kKMelPad / 8;           // 34 16-byte K chunks per row
+constexpr int kA1Sbo = kA1Chunks * 128;           // 4352
+constexpr int kESbo = 32 * 128;                   // enc / Oflat: K = 256 -> 32 chunks
+constexpr int kPSbo = 10 * 128;                   // P / vT tiles: K = 80 -> 10 chunks
+constexpr int kPTile = 16 * kPSbo;                // 20480
+constexpr int kStagesG1 = 9, kStagesTile = 4;
+constexpr int kStagesPerWindow = kStagesG1 + 5 * kStagesTile;  // 29
+
+// shared memory map (bytes)
+constexpr int kOffBar = 0;                        // mbarriers + tmem base
+constexpr int kOffConst = 256;                    // bc, ln_g, ln_b, bv (256 each), ba, w2 (128 each)
+constexpr int kOffX = kOffConst + 1280 * 4;       // A1 (43520) / P tiles (40960)
+constexpr int kOffE = kOffX + 10 * kA1Sbo;        // enc (40960) / Oflat
+constexpr int kOffVT = kOffE + 10 * kESbo;        // vT tiles (40960)
+constexpr int kOffRing = kOffVT + 2 * kPTile;
+constexpr int kSmemBytes = kOffRing + kRing * kStageBytes;   // 196352
+static_assert(kOffX % 128 == 0 && kOffE % 128 == 0 && kOffVT % 128 == 0 && kOffRing % 128 == 0, "alignment");
+static_assert(kOffX + 16 * kA1Sbo <= kSmemBytes && kOffE + 16 * kESbo <= kSmemBytes, "operand over-read stays inside");
+
+// TMEM column map
+constexpr uint32_t kColD1 = 0, kColS = 256, kColVT = 0, kColO = 160, kColH = 0;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug traps (error to the host) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && spin > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets row (lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, no swizzle, K-major: start>>4 | LBO>>4 << 16 | SBO>>4 << 32 | version 1 << 46
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&b);
+  o.z = *reinterpret_cast<uint32_t*>(&c);
+  o.w = *reinterpret_cast<uint32_t*>(&d);
+  return o;
+}
+
+__device__ __forceinline__ void simt_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const koe_core_weights& W = p.w;
+
+  // barriers: full[kRing], empty[kRing], mma_go, mma_done
+  const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kRing;
+  const uint32_t bar_go = bar_empty + 8 * kRing, bar_done = bar_go + 8;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 2));
+  float* s_red = reinterpret_cast<float*>(smem + kOffBar + 8 * (2 * kRing + 2) + 16);  // [8]
+  float* s_const = reinterpret_cast<float*>(smem + kOffConst);
+  const float *s_bc = s_const, *s_g = s_const + 256, *s_b = s_const + 512, *s_bv = s_const + 768;
+  const float *s_ba = s_const + 1024, *s_w2 = s_const + 1152;
+
+  if (tid == 0) {
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_go, kSimt);
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < kSimt) {
+    for (int i = tid; i < 256; i += kSimt) {
+      s_const[i] = W.bc[i];
+      s_const[256 + i] = W.ln_g[i];
+      s_const[512 + i] = W.ln_b[i];
+      s_const[768 + i] = W.bv[i];
+    }
+    s_const[1024 + tid] = W.ba[tid];
+    s_const[1152 + tid] = W.w2[tid];
+    // operand regions start as zeros so that never-written rows / K tails are finite
+    uint4* z = reinterpret_cast<uint4*>(smem + kOffX);
+    for (int i = tid; i < (kOffRing - kOffX) / 16; i += kSimt) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+        smem_u32((const void*)s_tmem)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  const int n_items = p.n_clips * p.n_out;
+  const int T = p.frames_per_window;
+
+  if (warp == 4) {
+    // =========================================================== TMA producer ==========================
+    if (lane == 0) {
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(W.tc_bf16);
+      uint32_t slot = 0, phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int s = 0; s < kStagesPerWindow; ++s) {
+          mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+          mbar_expect_tx(bar_full + 8 * slot, kStageBytes);
+          bulk_g2s(sbase + kOffRing + slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
+                   bar_full + 8 * slot);
+          if (++slot == kRing) slot = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =========================================================== MMA issuer ============================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0, go_phase = 0;
+      const uint32_t ring = sbase + kOffRing;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        // ---- G1: 9 stages of [256 x 32] weights; the last stage carries K = 256..271 only
+        mbar_wait(bar_go, go_phase), go_phase ^= 1;
+        tc_fence_after();
+        for (int s = 0; s < kStagesG1; ++s) {
+          mbar_wait(bar_full + 8 * slot, phase);
+          tc_fence_after();
+          const int nk = s == kStagesG1 - 1 ? 1 : 2;
+          for (int j = 0; j < nk; ++j) {
+            const uint64_t a = smem_desc(sbase + kOffX + (s * 2 + j) * 256, 128, kA1Sbo);
+            const uint64_t b = smem_desc(ring + slot * kStageBytes + j * 256, 128, 4 * 128);
+            tc_mma_bf16(tmem + kColD1, a, b, idesc_bf16(128, 256), (s | j) != 0);
+          }
+          tc_commit(bar_empty + 8 * slot);
+          if (++slot == kRing) slot = 0, phase ^= 1;
+        }
+        tc_commit(bar_done);
+        // ---- S (2 tiles) and VT (2 tiles): A = weight stage [128 x 64], B = enc [80 x 256]
+        mbar_wait(bar_go, go_phase), go_phase ^= 1;
+        tc_fence_after();
+        for (int tile = 0; tile < 4; ++tile) {
+          const uint32_t d = tmem + (tile < 2 ? kColS + 80 * tile : kColVT + 80 * (tile - 2));
+          for (int s = 0; s < kStagesTile; ++s) {
+            mbar_wait(bar_full + 8 * slot, phase);
+            tc_fence_after();
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t a = smem_desc(ring + slot * kStageBytes + j * 256, 128, 8 * 128);
+              const uint64_t b = smem_desc(sbase + kOffE + (s * 4 + j) * 256, 128, kESbo);
+              tc_mma_bf16(d, a, b, idesc_bf16(128, 80), (s | j) != 0);
+            }
+            tc_commit(bar_empty + 8 * slot);
+            if (++slot == kRing) slot = 0, phase ^= 1;
+          }
+        }
+        tc_commit(bar_done);
+        // ---- PV: A = P tile [128 x 80], B = vT tile [128 x 80]
+        mbar_wait(bar_go, go_phase), go_phase ^= 1;
+        tc_fence_after();
+        for (int t = 0; t < 2; ++t)
+          for (int j = 0; j < 5; ++j) {
+            const uint64_t a = smem_desc(sbase + kOffX + t * kPTile + j * 256, 128, kPSbo);
+            const uint64_t b = smem_desc(sbase + kOffVT + t * kPTile + j * 256, 128, kPSbo);
+            tc_mma_bf16(tmem + kColO + 128 * t, a, b, idesc_bf16(128, 128), j != 0);
+          }
+        tc_commit(bar_done);
+        // ---- H1: A = Oflat [128(28) x 256], B = weight stage [128 x 64]
+        mbar_wait(bar_go, go_phase), go_phase ^= 1;
+        tc_fence_after();
+        for (int s = 0; s < kStagesTile; ++s) {
+          mbar_wait(bar_full + 8 * slot, phase);
+          tc_fence_after();
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t a = smem_desc(sbase + kOffE + (s * 4 + j) * 256, 128, kESbo);
+            const uint64_t b = smem_desc(ring + slot * kStageBytes + j * 256, 128, 8 * 128);
+            tc_mma_bf16(tmem + kColH, a, b, idesc_bf16(128, 128), (s | j) != 0);
+          }
+          tc_commit(bar_empty + 8 * slot);
+          if (++slot == kRing) slot = 0, phase ^= 1;
+        }
+        tc_commit(bar_done);
+      }
+    }
+  } else {
+    // =========================================================== SIMT warps 0-3 ========================
+    uint32_t done_phase = 0;
+    const uint32_t lane_taddr = tmem + ((uint32_t)(32 * warp) << 16);  // this warp's TMEM lane quarter
+    const bool prenorm = p.mel_long != nullptr;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / p.n_out, wi = item % p.n_out;
+      // ---- window dB reference
+      float ref_db = 0.0f;
+      if (!prenorm) {
+        float mx = 0.0f;
+        for (int k = tid; k < T; k += kSimt) {
+          const int v = window_variant(p, k);
+          mx = fmaxf(mx, p.fmax[v][window_row(p, v, b, wi, k)]);
+        }
+        mx = warp_max(mx);
+        if (lane == 0) s_red[warp] = mx;
+        simt_barrier();
+        ref_db = power_db(fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3])));
+        simt_barrier();
+      }
+      // ---- A1: Xn[channel j][time t] as bf16, 8 consecutive frames of one channel per 16-byte store
+      for (int idx = tid; idx < kA1Chunks * kTok; idx += kSimt) {
+        const int c = idx / kTok, j = idx % kTok;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int t = 8 * c + e;
+          float x = 0.0f;
+          if (t < kKMel) {
+            if (prenorm) {
+              if (t >= p.mel_seq)
+                x = __ldg(p.mel_short + ((size_t)b * 3 + (t - p.mel_seq)) * kTok + j);
+              else if (t < p.n_long)
+                x = __ldg(p.mel_long + ((size_t)b * p.n_frames + t) * kTok + j);
+            } else {
+              int k;
+              if (t < p.mel_seq)
+                k = t < T ? t : -1;
+              else {
+                const int s = t - p.mel_seq;
+                k = T >= 3 ? T - 3 + s : (s < T ? s : -1);
+              }
+              if (k >= 0) {
+                const int var = window_variant(p, k);
+                x = normalise_db(__ldg(p.power[var] + window_row(p, var, b, wi, k) * kTok + j), ref_db, true);
+              }
+            }
+          }
+          v[e] = x;
+        }
+        *reinterpret_cast<uint4*>(smem + kOffX + (j >> 3) * kA1Sbo + c * 128 + (j & 7) * 16) = pack8_bf16(v);
+      }
+      fence_async_smem();
+      mbar_arrive(bar_go);
+
+      // ---- E1: bias + LayerNorm of token row tid -> enc (bf16, K-major) -------------------------------
+      mbar_wait(bar_done, done_phase), done_phase ^= 1;
+      tc_fence_after();
+      if (32 * warp < kTok) {  // warp-uniform: tcgen05.ld is warp-collective; warp 3 owns only padding rows
+        float sum = 0.0f;
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          float v[32];
+          tmem_ld32(lane_taddr + kColD1 + c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum += v[i] + s_bc[c0 + i];
+        }
+        const float mean = sum * (1.0f / 256);
+        float sq = 0.0f;
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          float v[32];
+          tmem_ld32(lane_taddr + kColD1 + c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float d = v[i] + s_bc[c0 + i] - mean;
+            sq = fmaf(d, d, sq);
+          }
+        }
+        const float rstd = rsqrtf(sq * (1.0f / 256) + W.ln_eps);
+        unsigned char* erow = smem + kOffE + (tid >> 3) * kESbo + (tid & 7) * 16;
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          float v[32];
+          tmem_ld32(lane_taddr + kColD1 + c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = (v[i] + s_bc[c0 + i] - mean) * rstd * s_g[c0 + i] + s_b[c0 + i];
+          if (tid < kTok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(erow + (c0 / 8 + q) * 128) = pack8_bf16(v + 8 * q);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      mbar_arrive(bar_go);
+
+      // ---- E2 softmax rows -> P tiles;  E3 vT rows (+ bv) -> vT tiles ---------------------------------
+      mbar_wait(bar_done, done_phase), done_phase ^= 1;
+      tc_fence_after();
+      for (int t = 0; t < 2; ++t) {
+        // row tid of tile t is (head 4 t + warp, query lane); queries 28..31 are padding
+        float s[kTok];
+        {
+          float v[32];
+          tmem_ld32(lane_taddr + kColS + 80 * t, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] = v[i];
+          tmem_ld32(lane_taddr + kColS + 80 * t + 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[32 + i] = v[i];
+          float u[16];
+          tmem_ld16(lane_taddr + kColS + 80 * t + 64, u);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s[64 + i] = u[i];
+        }
+        float m = s[0];
+#pragma unroll
+        for (int i = 1; i < kTok; ++i) m = fmaxf(m, s[i]);
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kTok; ++i) {
+          s[i] = expf(s[i] - m);
+          sum += s[i];
+        }
+        const float inv = lane < KOE_N_MOUTH ? 1.0f / sum : 0.0f;
+#pragma unroll
+        for (int i = 0; i < kTok; ++i) s[i] *= inv;
+        unsigned char* prow = smem + kOffX + t * kPTile + (tid >> 3) * kPSbo + (tid & 7) * 16;
+#pragma unroll
+        for (int c = 0; c < 10; ++c) *reinterpret_cast<uint4*>(prow + c * 128) = pack8_bf16(s + 8 * c);
+        if (p.attn_out != nullptr && lane < KOE_N_MOUTH) {
+          float* dst = p.attn_out + ((size_t)item * KOE_N_MOUTH + lane) * kTok;
+#pragma unroll
+          for (int i = 0; i < kTok; ++i) atomicAdd(dst + i, s[i] * (1.0f / KOE_N_HEADS));
+        }
+      }
+      for (int t = 0; t < 2; ++t) {
+        float s[kTok];
+        {
+          float v[32];
+          tmem_ld32(lane_taddr + kColVT + 80 * t, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] = v[i];
+          tmem_ld32(lane_taddr + kColVT + 80 * t + 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[32 + i] = v[i];
+          float u[16];
+          tmem_ld16(lane_taddr + kColVT + 80 * t + 64, u);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s[64 + i] = u[i];
+        }
+        const float bias = s_bv[128 * t + tid];
+#pragma unroll
+        for (int i = 0; i < kTok; ++i) s[i] += bias;
+        unsigned char* vrow = smem + kOffVT + t * kPTile + (tid >> 3) * kPSbo + (tid & 7) * 16;
+#pragma unroll
+        for (int c = 0; c < 10; ++c) *reinterpret_cast<uint4*>(vrow + c * 128) = pack8_bf16(s + 8 * c);
+      }
+      tc_fence_before();
+      fence_async_smem();
+      mbar_arrive(bar_go);
+
+      // ---- E4: O[h][q][0..31] (diagonal block of tile t) -> Oflat row q, K = 32 h + d -------------------
+      mbar_wait(bar_done, done_phase), done_phase ^= 1;
+      tc_fence_after();
+      for (int t = 0; t < 2; ++t) {
+        float v[32];
+        tmem_ld32(lane_taddr + kColO + 128 * t + 32 * warp, v);
+        if (lane < KOE_N_MOUTH) {
+          const int h = 4 * t + warp;
+          unsigned char* orow = smem + kOffE + (lane >> 3) * kESbo + (lane & 7) * 16 + (4 * h) * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(orow + q * 128) = pack8_bf16(v + 8 * q);
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      mbar_arrive(bar_go);
+
+      // ---- E5: decoder tail on rows 0..27 + fusion -----------------------------------------------------
+      mbar_wait(bar_done, done_phase), done_phase ^= 1;
+      tc_fence_after();
+      if (warp == 0) {
+        float logit = 0.0f;
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          float v[32];
+          tmem_ld32(lane_taddr + kColH + c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) logit = fmaf(fmaxf(v[i] + s_ba[c0 + i], 0.0f), s_w2[c0 + i], logit);
+        }
+        if (lane < KOE_N_MOUTH) {
+          const float y = 1.0f / (1.0f + expf(-(logit + W.b2)));
+          const int idx = __ldg(W.mouth_idx + lane);
+          const size_t o_off = (size_t)item * KOE_N_BLENDSHAPES + idx;
+          p.out[o_off] = fminf(fmaxf(__ldg(W.coef + idx) * y, 0.0f), 1.0f);
+          if (p.sigmoid_out != nullptr) p.sigmoid_out[o_off] = y;
+        }
+      } else if (warp == 1 && lane < KOE_N_EXPR) {
+        const float y = __ldg(p.expr_sigmoid + b);
+        const int idx = __ldg(W.expr_idx + lane);
+        const size_t o_off = (size_t)item * KOE_N_BLENDSHAPES + idx;
+        p.out[o_off] = fminf(fmaxf(__ldg(W.coef + idx) * y, 0.0f), 1.0f);
+        if (p.sigmoid_out != nullptr) p.sigmoid_out[o_off] = y;
+      }
+      tc_fence_before();
+      simt_barrier();  // the next window's A1 staging overwrites the P tiles only after every row is consumed
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  }
+}
+
+}  // namespace tc
+
+int launch_dual_stream_tc(const CoreParams& p, int precision, cudaStream_t stream) {
+  if (precision != 2)
+    return fail(KOE_E_UNSUPPORTED, "tensor-core path: only precision 2 (bf16 operands) is built; tf32 is not");
+  if (p.w.tc_bf16 == nullptr || p.w.tc_stages != tc::kStagesPerWindow)
+    return fail(KOE_E_INVALID, "tensor-core path: koe_core_weights.tc_bf16 is missing (%d stages, need %d)",
+                p.w.tc_stages, tc::kStagesPerWindow);
+  if (p.w.k_mel != tc::kKMel)
+    return fail(KOE_E_UNSUPPORTED, "tensor-core path is built for k_mel = 259 (30 fps); got %d", p.w.k_mel);
+  static int num_sms[64] = {0};
+  int dev = 0;
+  KOE_CUDA(cudaGetDevice(&dev));
+  KOE_REQUIRE(dev >= 0 && dev < 64, "device index too large");
+  if (num_sms[dev] == 0) {
+    KOE_CUDA(cudaFuncSetAttribute(tc::dual_stream_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tc::kSmemBytes));
+    int n = 0;
+    KOE_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    num_sms[dev] = n;
+  }
+  if (p.attn_out != nullptr)  // head-average is accumulated with atomics
+    KOE_CUDA(cudaMemsetAsync(p.attn_out, 0, (size_t)p.n_clips * p.n_out * KOE_N_MOUTH * tc::kTok * sizeof(float),
+                             stream));
+  const int grid = std::min(p.n_clips * p.n_out, num_sms[dev]);
+  tc::dual_stream_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(p);
+  count_launch();
+  KOE_CUDA(cudaGetLastError());
+  return KOE_OK;
+}
+
 }  // namespace koe

@@ -29,6 +29,24 @@ MOUTH_INDICES = list(range(14, 41)) + [51]          # dual_stream_attention.py:4
 EXPRESSION_INDICES = [i for i in range(52) if i not in MOUTH_INDICES]  # :45
 
 
+TC_STAGE_BYTES = 16384
+
+
+def _tile_kmajor(mat: torch.Tensor, rows_per_stage: int, k_per_stage: int, k_pad: int):
+    """Cut a [rows, K] matrix into pipeline-stage images in the UMMA no-swizzle K-major core-matrix layout:
+    inside a stage, element (r, k) sits at (r//8)*(chunks*128) + (k//8)*128 + (r%8)*16 + (k%8)*2 bytes (bf16)."""
+    rows, k = mat.shape
+    m = torch.zeros(rows, k_pad, dtype=mat.dtype, device=mat.device)
+    m[:, :k] = mat
+    out = []
+    for r0 in range(0, rows, rows_per_stage):
+        for k0 in range(0, k_pad, k_per_stage):
+            sub = m[r0:r0 + rows_per_stage, k0:k0 + k_per_stage]
+            img = sub.reshape(rows_per_stage // 8, 8, k_per_stage // 8, 8).permute(0, 2, 1, 3).contiguous()
+            out.append(img.reshape(-1))
+    return out
+
+
 def _ceil_to(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -45,6 +63,9 @@ class CoreWeights:
         for name in ("wc_t", "bc", "ln_g", "ln_b", "qk_t", "wv_t", "bv", "wa_t", "ba", "w2", "coef", "mouth_idx",
                      "expr_idx", "we1_t", "be1", "eln_g", "eln_b", "we2_t", "be2"):
             setattr(s, name, tensors[name].data_ptr())
+        tc = tensors.get("tc_bf16")
+        s.tc_bf16 = tc.data_ptr() if tc is not None else None
+        s.tc_stages = 0 if tc is None else tc.numel() * 2 // TC_STAGE_BYTES
         self.struct = s
         self.device = tensors["wc_t"].device
 
@@ -110,5 +131,15 @@ def fold(sd: Dict[str, torch.Tensor], num_heads: int, temperature: float, device
         "eln_g": f32(g("emotion_norm.weight")), "eln_b": f32(g("emotion_norm.bias")),
         "we2_t": f32(we2.T), "be2": f32(be2),
     }
+    if k_mel == 259:
+        # tcgen05 path: stage images in consumption order -- Wc (9 x [256 x 32]), Qk tiles 0/1, Wv tiles 0/1,
+        # Wa (each 4 x [128 x 64]); Qk rows are re-indexed to 32*h + q (queries 28..31 of each head are zero rows)
+        qk_pad = torch.zeros(256, d, dtype=dd, device=device)
+        for h in range(num_heads):
+            qk_pad[32 * h:32 * h + nq] = qk[h * nq:(h + 1) * nq]
+        stages = _tile_kmajor(wc, 256, 32, 288) + _tile_kmajor(qk_pad, 128, 64, 256) + \
+            _tile_kmajor(wv, 128, 64, 256) + _tile_kmajor(wa, 128, 64, 256)
+        tensors["tc_bf16"] = torch.cat(stages).to(torch.bfloat16).contiguous()
+        assert tensors["tc_bf16"].numel() * 2 == 29 * TC_STAGE_BYTES
     b2 = float(sd["blendshape_decoder.3.bias"].detach().reshape(-1)[0])
     return CoreWeights(tensors, k_mel, emo_in, b2, eps)
