@@ -60,7 +60,7 @@ int koe_frontend_destroy(koe_frontend_t* fe);
 int koe_frontend_filterbank_host(const koe_frontend_t* fe, float* fb_host);
 
 /*
- * Mel *power* of n_frames frames of every clip.  Output row j is frame g = frame_offset + j*frame_step:
+ * Mel power, in dB, of n_frames frames of every clip.  Output row j is frame g = frame_offset + j*frame_step:
  * the 1024-sample periodic-Hann frame centred on sample g*hop (librosa center=True).  Samples outside
  * [0, n_samples) read as zero (librosa pad_mode="constant"); in addition, when lo_rel_hops != KOE_NO_EDGE
  * samples before (g + lo_rel_hops)*hop read as zero, and when hi_rel_hops != KOE_NO_EDGE samples at or
@@ -68,7 +68,8 @@ int koe_frontend_filterbank_host(const koe_frontend_t* fe, float* fb_host);
  * windows of SequentialDualStreamModel.forward (src/model/sequential_dual_stream_model.py:101-120):
  * a window starting at frame i sees frame i with lo_rel_hops=0 and frame i+W with hi_rel_hops=0.
  *   audio      [n_clips][audio_stride] float32
- *   power      [n_clips][n_frames][80] float32   (sum_k fb[m][k] * |X_g[k]|^2)
+ *   power      [n_clips][n_frames][80] float32   10*log10(max(sum_k fb[m][k] * |X_g[k]|^2, 1e-10)): the first term of
+ *                                                librosa.power_to_db, so that a consumer only subtracts its reference
  *   frame_max  [n_clips][n_frames]     float32   (max_m power[.,j,m]); may be NULL
  */
 int koe_logmel_power(const koe_frontend_t* fe, const float* audio, int64_t audio_stride, int n_clips,
@@ -76,7 +77,7 @@ int koe_logmel_power(const koe_frontend_t* fe, const float* audio, int64_t audio
                      int hi_rel_hops, float* power, float* frame_max, void* stream);
 
 /*
- * power_to_db(ref = max over the clip's n_frames frames, amin=1e-10, top_db=80) followed by (x+80)/80.
+ * Rest of power_to_db on koe_logmel_power's output (ref = max over the clip's n_frames frames, top_db=80), then (x+80)/80.
  * Writes the long-term features [n_clips][n_frames][80] and the short-term detail = last three frames
  * [n_clips][3][80] (zero rows when n_frames < 3: simplified_dual_stream_model.py:206-212).
  * db_only != 0 skips the (x+80)/80 rescale (MelSlidingWindowExtractor semantics, mel_sliding_window.py:295).

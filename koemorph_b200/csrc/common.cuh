@@ -61,9 +61,9 @@ constexpr float kAmin = 1e-10f;
 constexpr float kTopDb = 80.0f;
 
 __device__ __forceinline__ float power_db(float p) { return 10.0f * log10f(fmaxf(p, kAmin)); }
-// dB relative to ref_db, clamped at -top_db, optionally rescaled to [0, 1] by (x + 80) / 80
-__device__ __forceinline__ float normalise_db(float p, float ref_db, bool rescale) {
-  float x = fmaxf(power_db(p) - ref_db, -kTopDb);
+// dB value relative to ref_db, clamped at -top_db, optionally rescaled to [0, 1] by (x + 80) / 80
+__device__ __forceinline__ float normalise_db(float db, float ref_db, bool rescale) {
+  float x = fmaxf(db - ref_db, -kTopDb);
   return rescale ? (x + 80.0f) / 80.0f : x;
 }
 

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kCoreThreads, 1) dual_stream_fp32_kernel(CoreP
     // ---- P0: dB reference of this window -------------------------------------------------------
     float ref_db = 0.0f;
     if (!prenorm) {
-      float mx = 0.0f;
+      float mx = -INFINITY;
       for (int k = tid; k < T; k += kCoreThreads) {
         const int v = window_variant(p, k);
         mx = fmaxf(mx, p.fmax[v][window_row(p, v, b, wi, k)]);
@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(kCoreThreads, 1) dual_stream_fp32_kernel(CoreP
       if (tx == 0) s_red[ty] = mx;
       __syncthreads();
       if (tid < 32) {
-        float v = tid < 8 ? s_red[tid] : 0.0f;
+        float v = tid < 8 ? s_red[tid] : -INFINITY;
         v = warp_max(v);
-        if (tid == 0) s_red[8] = power_db(v);
+        if (tid == 0) s_red[8] = v;
       }
       __syncthreads();
       ref_db = s_red[8];

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       // ---- window dB reference
       float ref_db = 0.0f;
       if (!prenorm) {
-        float mx = 0.0f;
+        float mx = -INFINITY;
         for (int k = tid; k < T; k += kSimt) {
           const int v = window_variant(p, k);
           mx = fmaxf(mx, p.fmax[v][window_row(p, v, b, wi, k)]);
@@ -304,40 +304,77 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         mx = warp_max(mx);
         if (lane == 0) s_red[warp] = mx;
         simt_barrier();
-        ref_db = power_db(fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3])));
+        ref_db = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
         simt_barrier();
       }
-      // ---- A1: Xn[channel j][time t] as bf16, 8 consecutive frames of one channel per 16-byte store
-      for (int idx = tid; idx < kA1Chunks * kTok; idx += kSimt) {
-        const int c = idx / kTok, j = idx % kTok;
-        float v[8];
+      // ---- A1: Xn[channel j][time t] as bf16.  One item = 8 consecutive frames x 4 consecutive channels:
+      // 8 independent 16-byte loads (frame rows are 320 B apart), then one 16-byte store per channel.
+      // Two items are in flight per thread so that ~32 KB of loads per CTA hide the L2 latency.
+      {
+        constexpr int kQuads = kTok / 4;                 // 20 channel quads per frame
+        constexpr int kItems = kA1Chunks * kQuads;       // 680
+        auto load_item = [&](int idx, float4 (&r)[8]) {
+          const int c = idx / kQuads, q = idx % kQuads;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int t = 8 * c + e;
-          float x = 0.0f;
-          if (t < kKMel) {
+          for (int e = 0; e < 8; ++e) {
+            const int t = 8 * c + e;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < kKMel) {
+              if (prenorm) {
+                if (t >= p.mel_seq)
+                  x = __ldg(reinterpret_cast<const float4*>(p.mel_short + ((size_t)b * 3 + (t - p.mel_seq)) * kTok) + q);
+                else if (t < p.n_long)
+                  x = __ldg(reinterpret_cast<const float4*>(p.mel_long + ((size_t)b * p.n_frames + t) * kTok) + q);
+              } else {
+                int k;
+                if (t < p.mel_seq)
+                  k = t < T ? t : -1;
+                else {
+                  const int s = t - p.mel_seq;
+                  k = T >= 3 ? T - 3 + s : (s < T ? s : -1);
+                }
+                if (k >= 0) {
+                  const int var = window_variant(p, k);
+                  x = __ldg(reinterpret_cast<const float4*>(p.power[var] + window_row(p, var, b, wi, k) * kTok) + q);
+                } else {
+                  x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);  // zero padding: normalises to 0
+                }
+              }
+            } else if (!prenorm) {
+              x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+            r[e] = x;
+          }
+        };
+        auto store_item = [&](int idx, const float4 (&r)[8]) {
+          const int c = idx / kQuads, q = idx % kQuads;
+          float v[4][8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
             if (prenorm) {
-              if (t >= p.mel_seq)
-                x = __ldg(p.mel_short + ((size_t)b * 3 + (t - p.mel_seq)) * kTok + j);
-              else if (t < p.n_long)
-                x = __ldg(p.mel_long + ((size_t)b * p.n_frames + t) * kTok + j);
+              v[0][e] = r[e].x, v[1][e] = r[e].y, v[2][e] = r[e].z, v[3][e] = r[e].w;
             } else {
-              int k;
-              if (t < p.mel_seq)
-                k = t < T ? t : -1;
-              else {
-                const int s = t - p.mel_seq;
-                k = T >= 3 ? T - 3 + s : (s < T ? s : -1);
-              }
-              if (k >= 0) {
-                const int var = window_variant(p, k);
-                x = normalise_db(__ldg(p.power[var] + window_row(p, var, b, wi, k) * kTok + j), ref_db, true);
-              }
+              const bool real = 8 * c + e < kKMel;       // K tail 259..271 must be exact zeros
+              v[0][e] = real ? normalise_db(r[e].x, ref_db, true) : 0.0f;
+              v[1][e] = real ? normalise_db(r[e].y, ref_db, true) : 0.0f;
+              v[2][e] = real ? normalise_db(r[e].z, ref_db, true) : 0.0f;
+              v[3][e] = real ? normalise_db(r[e].w, ref_db, true) : 0.0f;
             }
           }
-          v[e] = x;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = 4 * q + i;
+            *reinterpret_cast<uint4*>(smem + kOffX + (j >> 3) * kA1Sbo + c * 128 + (j & 7) * 16) = pack8_bf16(v[i]);
+          }
+        };
+        for (int idx = tid; idx < kItems; idx += 2 * kSimt) {
+          float4 r0[8], r1[8];
+          const bool two = idx + kSimt < kItems;
+          load_item(idx, r0);
+          if (two) load_item(idx + kSimt, r1);
+          store_item(idx, r0);
+          if (two) store_item(idx + kSimt, r1);
         }
-        *reinterpret_cast<uint4*>(smem + kOffX + (j >> 3) * kA1Sbo + c * 128 + (j & 7) * 16) = pack8_bf16(v);
       }
       fence_async_smem();
       mbar_arrive(bar_go);

@@ -30,19 +30,18 @@ constexpr int kThreads = kWarps * 32;
 constexpr int kSlots = 2 * kWarps;      // frames per CTA iteration
 constexpr int kXbufStride = 1058;       // floats per warp buffer: >= 32*33, == 2 (mod 32)
 constexpr int kSecondFrame = 513;       // offset of the warp's second spectrum, == 1 (mod 32)
-constexpr int kMaxNnz = 1024;
-constexpr int kPairs = KOE_N_MELS / 2;  // 40 pairs of adjacent filters
-constexpr int kTileStride = 84;         // output staging row stride (floats): float4-aligned, bank-skewed
+constexpr int kMaxBins = 512;           // spectrum bins that carry filterbank weight (507 for 80..8000 Hz)
+constexpr int kRuns = 2 * kWarps;       // the weighted bins are cut into 16 equal runs, two per warp
+constexpr int kTileStride = 81;         // mel accumulator row stride (floats), odd: conflict-free across slots
 
 struct FrontendTables {
   const float* hann;     // [1024]
   const float2* tw;      // [32][32] W_1024^(k1*n2)
-  const float* melw;     // packed non-zero filter weights
-  const int* mstart;     // [80]
-  const int* mlen;       // [80]
-  const int* moff;       // [80]
-  const int* order;      // [40] pair processing order (longest first, dealt round-robin to warps)
-  int nnz;
+  // Slaney filterbank, bin-major: a spectrum bin feeds at most two ADJACENT filters (fl, fl + 1)
+  const float2* binw;    // [n_bins] (weight into filter fl, weight into filter fl + 1)
+  const int* binkf;      // [n_bins] bin index k | fl << 16
+  const int* runs;       // [kRuns + 1] run boundaries into the bin list
+  int n_bins;
 };
 
 struct LogmelParams {
@@ -128,26 +127,21 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_hann = reinterpret_cast<float*>(smem_raw);              // 1024
   float2* s_tw = reinterpret_cast<float2*>(s_hann + kFrameLen);    // 1024 float2
-  float* s_melw = reinterpret_cast<float*>(s_tw + 1024);           // kMaxNnz
-  int* s_mstart = reinterpret_cast<int*>(s_melw + kMaxNnz);        // 80
-  int* s_mlen = s_mstart + KOE_N_MELS;                             // 80
-  int* s_moff = s_mlen + KOE_N_MELS;                               // 80
-  int* s_order = s_moff + KOE_N_MELS;                              // 40
-  float* s_xbuf = reinterpret_cast<float*>(s_order + kPairs + 8);  // kWarps * kXbufStride
-  float* s_tile = s_xbuf + kWarps * kXbufStride;                   // kSlots * 80
-  float* s_wmax = s_tile + kSlots * kTileStride;                    // kWarps * 16
+  float2* s_binw = s_tw + 1024;                                    // kMaxBins float2
+  int* s_binkf = reinterpret_cast<int*>(s_binw + kMaxBins);        // kMaxBins
+  int* s_runs = s_binkf + kMaxBins;                                // kRuns + 1 (+ pad to 24)
+  float* s_xbuf = reinterpret_cast<float*>(s_runs + 24);           // kWarps * kXbufStride
+  float* s_tile = s_xbuf + kWarps * kXbufStride;                   // kSlots * kTileStride mel accumulators
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int i = tid; i < kFrameLen; i += kThreads) s_hann[i] = tab.hann[i];
   for (int i = tid; i < 1024; i += kThreads) s_tw[i] = tab.tw[i];
-  for (int i = tid; i < tab.nnz; i += kThreads) s_melw[i] = tab.melw[i];
-  if (tid < KOE_N_MELS) {
-    s_mstart[tid] = tab.mstart[tid];
-    s_mlen[tid] = tab.mlen[tid];
-    s_moff[tid] = tab.moff[tid];
+  for (int i = tid; i < tab.n_bins; i += kThreads) {
+    s_binw[i] = tab.binw[i];
+    s_binkf[i] = tab.binkf[i];
   }
-  if (tid < kPairs) s_order[tid] = tab.order[tid];
+  if (tid <= kRuns) s_runs[tid] = tab.runs[tid];
   __syncthreads();
 
   const int ppc = (p.n_frames + 1) >> 1;  // frame pairs per clip
@@ -156,6 +150,7 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   float* xb = s_xbuf + warp * kXbufStride;
 
   for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    for (int i = tid; i < kSlots * kTileStride; i += kThreads) s_tile[i] = 0.0f;  // consumed after two barriers
     // ------------------------------------------------------------------ FFT phase (per warp)
     const long long pair = blk * kWarps + warp;
     if (pair < total_pairs) {
@@ -178,14 +173,27 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
       const int sb0 = fb * p.hop - kFrameLen / 2 + lane;
 
       float re[32], im[32];
+      const int fa_lo = fa * p.hop - kFrameLen / 2, fb_lo = fb * p.hop - kFrameLen / 2;
+      if (fa_lo >= lo_a && fa_lo + kFrameLen <= hi_a && fb_lo >= lo_b && fb_lo + kFrameLen <= hi_b) {
+        // interior frames (all but the first / last of a clip): no masking, one base pointer per frame
+        const float* __restrict__ pa = clip + sa0;
+        const float* __restrict__ pb = clip + sb0;
 #pragma unroll
-      for (int n1 = 0; n1 < 32; ++n1) {
-        const int sa = sa0 + 32 * n1, sb = sb0 + 32 * n1;
-        const float w = s_hann[32 * n1 + lane];
-        const float va = (sa >= lo_a && sa < hi_a) ? __ldg(clip + sa) : 0.0f;
-        const float vb = (sb >= lo_b && sb < hi_b) ? __ldg(clip + sb) : 0.0f;
-        re[n1] = va * w;
-        im[n1] = vb * w;
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const float w = s_hann[32 * n1 + lane];
+          re[n1] = __ldg(pa + 32 * n1) * w;
+          im[n1] = __ldg(pb + 32 * n1) * w;
+        }
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const int sa = sa0 + 32 * n1, sb = sb0 + 32 * n1;
+          const float w = s_hann[32 * n1 + lane];
+          const float va = (sa >= lo_a && sa < hi_a) ? __ldg(clip + sa) : 0.0f;
+          const float vb = (sb >= lo_b && sb < hi_b) ? __ldg(clip + sb) : 0.0f;
+          re[n1] = va * w;
+          im[n1] = vb * w;
+        }
       }
       fft32(re, im);  // element i = Y[k1 = bitrev5(i)] for column n2 = lane
 #pragma unroll
@@ -243,58 +251,60 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
     __syncthreads();
 
     // ------------------------------------------------------------------ mel phase (whole CTA)
+    // lane = (frame slot, run): walk the run's bins once, feeding the two adjacent filters each bin touches;
+    // runs are cut on interval boundaries, so a filter receives at most two partial sums (its rising half from one
+    // run, its falling half from the same or the next) and the float atomics are order-free: 0 + a + b == 0 + b + a.
     {
-      const int slot = lane & 15, which = lane >> 4;
+      const int slot = lane & 15, run = 2 * warp + (lane >> 4);
       const float* spec = s_xbuf + (slot >> 1) * kXbufStride + (slot & 1) * kSecondFrame;
-      float lane_max = 0.0f;
-#pragma unroll 1
-      for (int it = 0; it < kPairs / kWarps; ++it) {
-        const int m = 2 * s_order[warp + kWarps * it] + which;
-        const int start = s_mstart[m], len = s_mlen[m];
-        const float* w = s_melw + s_moff[m];
-        const float* x = spec + start;
-        float acc0 = 0.0f, acc1 = 0.0f;
-        int j = 0;
-        for (; j + 1 < len; j += 2) {
-          acc0 = fmaf(w[j], x[j], acc0);
-          acc1 = fmaf(w[j + 1], x[j + 1], acc1);
+      float* trow = s_tile + slot * kTileStride;
+      int i = s_runs[run];
+      const int iend = s_runs[run + 1];
+      int fl = i < iend ? (s_binkf[i] >> 16) : 0;
+      float acc_lo = 0.0f, acc_hi = 0.0f;
+      for (; i < iend; ++i) {
+        const int kf = s_binkf[i];
+        const int f = kf >> 16;
+        if (f != fl) {
+          atomicAdd(trow + fl, acc_lo);
+          if (f == fl + 1) {
+            acc_lo = acc_hi;
+          } else {
+            if (fl + 1 < KOE_N_MELS) atomicAdd(trow + fl + 1, acc_hi);
+            acc_lo = 0.0f;
+          }
+          acc_hi = 0.0f;
+          fl = f;
         }
-        if (j < len) acc0 = fmaf(w[j], x[j], acc0);
-        const float acc = acc0 + acc1;
-        s_tile[slot * kTileStride + m] = acc;
-        lane_max = fmaxf(lane_max, acc);
+        const float2 w = s_binw[i];
+        const float x = spec[kf & 0xffff];
+        acc_lo = fmaf(w.x, x, acc_lo);
+        acc_hi = fmaf(w.y, x, acc_hi);
       }
-      lane_max = fmaxf(lane_max, __shfl_xor_sync(kFullMask, lane_max, 16));
-      if (lane < 16) s_wmax[warp * 16 + lane] = lane_max;
+      atomicAdd(trow + fl, acc_lo);
+      if (fl + 1 < KOE_N_MELS) atomicAdd(trow + fl + 1, acc_hi);
     }
     __syncthreads();
 
-    // ------------------------------------------------------------------ store phase
+    // ------------------------------------------------------------------ store phase: warp w owns slots 2w, 2w+1
     {
-      // slot s -> pair blk*8 + (s>>1), frame 2*(pair % ppc) + (s & 1)
-      for (int idx = tid; idx < kSlots * (KOE_N_MELS / 4); idx += kThreads) {
-        const int s = idx / (KOE_N_MELS / 4), q = idx % (KOE_N_MELS / 4);
-        const long long pr_ = blk * kWarps + (s >> 1);
-        if (pr_ < total_pairs) {
-          const int b = (int)(pr_ / ppc);
-          const int g = 2 * (int)(pr_ % ppc) + (s & 1);
-          if (g < p.n_frames) {
-            const float4 v = *reinterpret_cast<const float4*>(s_tile + s * kTileStride + 4 * q);
-            *reinterpret_cast<float4*>(p.power + ((long long)b * p.n_frames + g) * KOE_N_MELS + 4 * q) = v;
-          }
-        }
-      }
-      if (tid < kSlots && p.frame_max != nullptr) {
-        const int s = tid;
-        const long long pr_ = blk * kWarps + (s >> 1);
-        if (pr_ < total_pairs) {
-          const int b = (int)(pr_ / ppc);
-          const int g = 2 * (int)(pr_ % ppc) + (s & 1);
-          if (g < p.n_frames) {
-            float mx = 0.0f;
+      const long long pr_ = blk * kWarps + warp;
+      if (pr_ < total_pairs) {
+        const int b = (int)(pr_ / ppc);
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) mx = fmaxf(mx, s_wmax[w * 16 + s]);
-            p.frame_max[(long long)b * p.n_frames + g] = mx;
+        for (int h = 0; h < 2; ++h) {
+          const int g = 2 * (int)(pr_ % ppc) + h;
+          if (g < p.n_frames) {
+            const float* trow = s_tile + (2 * warp + h) * kTileStride;
+            float* dst = p.power + ((long long)b * p.n_frames + g) * KOE_N_MELS;
+            // stored in dB: 10 log10(max(power, amin)); the consumer only subtracts its reference and clamps
+            const float v0 = power_db(trow[lane]), v1 = power_db(trow[lane + 32]);
+            const float v2 = lane < 16 ? power_db(trow[lane + 64]) : -INFINITY;
+            dst[lane] = v0;
+            dst[lane + 32] = v1;
+            if (lane < 16) dst[lane + 64] = v2;
+            const float mx = warp_max(fmaxf(fmaxf(v0, v1), v2));
+            if (lane == 0 && p.frame_max != nullptr) p.frame_max[(long long)b * p.n_frames + g] = mx;
           }
         }
       }
@@ -303,9 +313,9 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   }
 }
 
-constexpr size_t kLogmelSmem = sizeof(float) * kFrameLen + sizeof(float2) * 1024 + sizeof(float) * kMaxNnz +
-                               sizeof(int) * (3 * KOE_N_MELS + kPairs + 8) +
-                               sizeof(float) * (kWarps * kXbufStride + kSlots * kTileStride + kWarps * 16);
+constexpr size_t kLogmelSmem = sizeof(float) * kFrameLen + sizeof(float2) * 1024 + sizeof(float2) * kMaxBins +
+                               sizeof(int) * (kMaxBins + 24) +
+                               sizeof(float) * (kWarps * kXbufStride + kSlots * kTileStride);
 
 // ---- dB normalisation: ref = clip max, clamp, rescale; emits long-term and last-3 short-term features
 __global__ void logmel_normalise_kernel(const float* __restrict__ power, const float* __restrict__ frame_max,
@@ -315,15 +325,15 @@ __global__ void logmel_normalise_kernel(const float* __restrict__ power, const f
   __shared__ float s_ref_db;
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* fm = frame_max + (long long)b * n_frames;
-  float mx = 0.0f;
+  float mx = -INFINITY;
   for (int g = tid; g < n_frames; g += blockDim.x) mx = fmaxf(mx, fm[g]);
   mx = warp_max(mx);
   if ((tid & 31) == 0) s_red[tid >> 5] = mx;
   __syncthreads();
   if (tid < 32) {
-    float v = tid < (blockDim.x >> 5) ? s_red[tid] : 0.0f;
+    float v = tid < (blockDim.x >> 5) ? s_red[tid] : -INFINITY;
     v = warp_max(v);
-    if (tid == 0) s_ref_db = power_db(v);
+    if (tid == 0) s_ref_db = v;
   }
   __syncthreads();
   const float ref_db = s_ref_db;
@@ -399,9 +409,9 @@ struct koe_frontend {
   float fmin = 0, fmax = 0;
   float* d_hann = nullptr;
   float2* d_tw = nullptr;
-  float* d_melw = nullptr;
-  int* d_tables = nullptr;  // mstart | mlen | moff | order
-  int nnz = 0;
+  float2* d_binw = nullptr;
+  int* d_tables = nullptr;  // binkf[kMaxBins] | runs[kRuns + 1]
+  int n_bins = 0;
   int num_sms = 0, occupancy = 0;
   std::vector<float> fb_host;
 };
@@ -431,39 +441,38 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
   fe->fmax = fmax;
   fe->fb_host = slaney_filterbank(sample_rate, n_fft, n_mels, fmin, fmax);
 
-  // sparse tables: each filter's non-zeros are one contiguous run of bins
-  std::vector<float> melw;
-  std::vector<int> tables(3 * KOE_N_MELS + kPairs, 0);
-  for (int m = 0; m < n_mels; ++m) {
-    int first = -1, last = -2;
-    for (int k = 0; k < kBins; ++k)
+  // bin-major sparse filterbank: every weighted bin feeds one filter or two adjacent ones
+  std::vector<float2> binw;
+  std::vector<int> tables(kMaxBins + kRuns + 1, 0);
+  for (int k = 0; k < kBins; ++k) {
+    int first = -1, count = 0, last = -1;
+    for (int m = 0; m < n_mels; ++m)
       if (fe->fb_host[(size_t)m * kBins + k] > 0.0f) {
-        if (first < 0) first = k;
-        last = k;
+        if (first < 0) first = m;
+        last = m;
+        ++count;
       }
-    if (first < 0) first = 0, last = -1;
-    tables[m] = first;
-    tables[KOE_N_MELS + m] = last - first + 1;
-    tables[2 * KOE_N_MELS + m] = (int)melw.size();
-    for (int k = first; k <= last; ++k) melw.push_back(fe->fb_host[(size_t)m * kBins + k]);
-  }
-  fe->nnz = (int)melw.size();
-  if (fe->nnz > kMaxNnz) {
-    delete fe;
-    cudaSetDevice(prev);
-    return fail(KOE_E_UNSUPPORTED, "koe_frontend_create: filterbank has %d non-zeros (max %d)", fe->nnz, kMaxNnz);
-  }
-  // pair order: sort pairs by cost (max length of the two filters), deal round-robin in serpentine order
-  {
-    std::vector<std::pair<int, int>> cost(kPairs);
-    for (int q = 0; q < kPairs; ++q)
-      cost[q] = {std::max(tables[KOE_N_MELS + 2 * q], tables[KOE_N_MELS + 2 * q + 1]), q};
-    std::sort(cost.begin(), cost.end(), [](auto& a, auto& b) { return a.first > b.first; });
-    for (int i = 0; i < kPairs; ++i) {
-      const int round = i / kWarps, pos = i % kWarps;
-      const int warp = (round & 1) ? kWarps - 1 - pos : pos;
-      tables[3 * KOE_N_MELS + warp + kWarps * round] = cost[i].second;
+    if (count == 0) continue;
+    if (count > 2 || last - first > 1 || (int)binw.size() >= kMaxBins) {
+      delete fe;
+      cudaSetDevice(prev);
+      return fail(KOE_E_UNSUPPORTED, "koe_frontend_create: filterbank is not a bank of adjacent triangles at bin %d", k);
     }
+    tables[binw.size()] = k | (first << 16);
+    binw.push_back(make_float2(fe->fb_host[(size_t)first * kBins + k],
+                               count == 2 ? fe->fb_host[(size_t)last * kBins + k] : 0.0f));
+  }
+  fe->n_bins = (int)binw.size();
+  // run boundaries on filter-interval boundaries (where fl changes), as balanced as that allows: then a
+  // filter's rising half lies in one run and its falling half in the same or the next run -> <= 2 partial sums
+  {
+    int r = 1;
+    tables[kMaxBins] = 0;
+    for (int i = 1; i < fe->n_bins && r < kRuns; ++i) {
+      const bool boundary = (tables[i] >> 16) != (tables[i - 1] >> 16);
+      if (boundary && (long long)i * kRuns >= (long long)fe->n_bins * r) tables[kMaxBins + r++] = i;
+    }
+    for (; r <= kRuns; ++r) tables[kMaxBins + r] = fe->n_bins;
   }
   std::vector<float> hann(kFrameLen);
   for (int n = 0; n < kFrameLen; ++n) hann[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / kFrameLen));
@@ -481,8 +490,8 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
   };
   up((void**)&fe->d_hann, hann.data(), hann.size() * sizeof(float));
   up((void**)&fe->d_tw, tw.data(), tw.size() * sizeof(float2));
-  melw.resize(kMaxNnz, 0.0f);
-  up((void**)&fe->d_melw, melw.data(), melw.size() * sizeof(float));
+  binw.resize(kMaxBins, make_float2(0.f, 0.f));
+  up((void**)&fe->d_binw, binw.data(), binw.size() * sizeof(float2));
   up((void**)&fe->d_tables, tables.data(), tables.size() * sizeof(int));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(logmel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelSmem);
@@ -506,7 +515,7 @@ extern "C" int koe_frontend_destroy(koe_frontend_t* fe) {
   if (fe == nullptr) return KOE_OK;
   cudaFree(fe->d_hann);
   cudaFree(fe->d_tw);
-  cudaFree(fe->d_melw);
+  cudaFree(fe->d_binw);
   cudaFree(fe->d_tables);
   delete fe;
   return KOE_OK;
@@ -533,12 +542,10 @@ extern "C" int koe_logmel_power(const koe_frontend_t* fe, const float* audio, in
   FrontendTables tab;
   tab.hann = fe->d_hann;
   tab.tw = fe->d_tw;
-  tab.melw = fe->d_melw;
-  tab.mstart = fe->d_tables;
-  tab.mlen = fe->d_tables + KOE_N_MELS;
-  tab.moff = fe->d_tables + 2 * KOE_N_MELS;
-  tab.order = fe->d_tables + 3 * KOE_N_MELS;
-  tab.nnz = fe->nnz;
+  tab.binw = fe->d_binw;
+  tab.binkf = fe->d_tables;
+  tab.runs = fe->d_tables + kMaxBins;
+  tab.n_bins = fe->n_bins;
   LogmelParams p;
   p.audio = audio;
   p.audio_stride = audio_stride;

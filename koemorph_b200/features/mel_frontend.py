@@ -61,7 +61,8 @@ class LogMelFrontend:
     def power(self, audio: torch.Tensor, hop: int, n_frames: int, frame_offset: int = 0, frame_step: int = 1,
               lo_rel: Optional[int] = None, hi_rel: Optional[int] = None,
               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """audio (B, L) float32 CUDA -> mel power (B, n_frames, 80), per-frame max (B, n_frames)."""
+        """audio (B, L) float32 CUDA -> mel power in dB, 10*log10(max(p, 1e-10)), (B, n_frames, 80) and its
+        per-frame max (B, n_frames)."""
         audio = _lib.require_cuda(audio, "audio")
         if audio.dim() != 2:
             raise ValueError(f"audio must be (B, L), got {tuple(audio.shape)}")
