@@ -52,7 +52,18 @@ def _cpu_pass(reps):
 def _cpu_pool(clips_per_worker):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    pool = mp.get_context("spawn").Pool(cores, initializer=_cpu_init, initargs=(clips_per_worker,))
+    # one single-threaded worker per core: without this every worker's BLAS/OpenMP runtime spawns a thread per core and
+    # the oversubscribed pool runs ~50x slower (which would flatter the GPU numbers)
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS")}
+    os.environ.update({k: "1" for k in saved})
+    try:
+        pool = mp.get_context("spawn").Pool(cores, initializer=_cpu_init, initargs=(clips_per_worker,))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     pool.map(_cpu_pass, [0] * cores, chunksize=1)  # make sure every worker is up
     return pool, cores
 

@@ -77,6 +77,27 @@ int koe_logmel_power(const koe_frontend_t* fe, const float* audio, int64_t audio
                      int hi_rel_hops, float* power, float* frame_max, void* stream);
 
 /*
+ * General form of koe_logmel_power for the streaming paths: frame j is centred on sample
+ * sample_offset + (frame_offset + j*frame_step)*hop (the window-edge masks move with it); pad_mode 1 reflects the
+ * clip about its first / last sample instead of zero padding (numpy "reflect", the default of
+ * MelSlidingWindowExtractor, src/features/mel_sliding_window.py:178,291); the output blocks of consecutive clips are
+ * power_clip_stride / frame_max_clip_stride elements apart, so rows can land directly in per-stream ring buffers.
+ */
+typedef struct {
+  const float* audio;
+  int64_t audio_stride;
+  int32_t n_clips, n_samples, hop, n_frames;
+  int32_t frame_offset, frame_step, sample_offset;
+  int32_t lo_rel_hops, hi_rel_hops;
+  int32_t pad_mode;
+  float* power;
+  int64_t power_clip_stride;
+  float* frame_max;
+  int64_t frame_max_clip_stride;
+} koe_logmel_args;
+int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_args* args, void* stream);
+
+/*
  * Rest of power_to_db on koe_logmel_power's output (ref = max over the clip's n_frames frames, top_db=80), then (x+80)/80.
  * Writes the long-term features [n_clips][n_frames][80] and the short-term detail = last three frames
  * [n_clips][3][80] (zero rows when n_frames < 3: simplified_dual_stream_model.py:206-212).
@@ -163,6 +184,20 @@ int koe_dual_stream_windows(const koe_core_weights* w, const float* const* power
 int koe_dual_stream_features(const koe_core_weights* w, const float* mel_long, int n_long, const float* mel_short,
                              int n_clips, const float* expr_sigmoid, float* out, float* sigmoid_out,
                              float* attn_out, int precision, void* stream);
+
+/*
+ * Streaming step (rt.py-style sliding window, stride one hop, all streams in lockstep): one window per stream whose
+ * frames live in per-stream rings of ring_frames mel rows.  Frame k of the window is
+ *   k == 0                      lo-edge row:  power_lo_ring[s][(ring_base) % ring_frames]
+ *   0 < k < frames_per_window-1 plain row:    power_ring  [s][(ring_base + k) % ring_frames]
+ *   k == frames_per_window-1    hi-edge row:  power_hi    [s]
+ * (30 fps geometry: hop >= n_fft/2, one edge frame per side).  Outputs as koe_dual_stream_windows with n_out = 1.
+ */
+int koe_dual_stream_ring(const koe_core_weights* w, const float* power_ring, const float* fmax_ring,
+                         const float* power_lo_ring, const float* fmax_lo_ring, const float* power_hi,
+                         const float* fmax_hi, int n_streams, int ring_frames, int ring_base, int frames_per_window,
+                         const float* expr_sigmoid, float* out, float* sigmoid_out, float* attn_out, int precision,
+                         void* stream);
 
 /*
  * Learnable-alpha exponential smoothing along the frame axis, in place

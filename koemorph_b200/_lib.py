@@ -34,6 +34,18 @@ class CoreWeightsStruct(C.Structure):
     ]
 
 
+class LogmelArgs(C.Structure):
+    """Mirror of ``koe_logmel_args`` (include/koemorph_b200.h)."""
+    _fields_ = [
+        ("audio", C.c_void_p), ("audio_stride", C.c_int64),
+        ("n_clips", C.c_int32), ("n_samples", C.c_int32), ("hop", C.c_int32), ("n_frames", C.c_int32),
+        ("frame_offset", C.c_int32), ("frame_step", C.c_int32), ("sample_offset", C.c_int32),
+        ("lo_rel_hops", C.c_int32), ("hi_rel_hops", C.c_int32), ("pad_mode", C.c_int32),
+        ("power", C.c_void_p), ("power_clip_stride", C.c_int64),
+        ("frame_max", C.c_void_p), ("frame_max_clip_stride", C.c_int64),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -48,6 +60,10 @@ _SIGNATURES = {
     "koe_frontend_filterbank_host": (C.c_int, [C.c_void_p, C.c_void_p]),
     "koe_logmel_power": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "koe_logmel_power_ex": (C.c_int, [C.c_void_p, C.POINTER(LogmelArgs), C.c_void_p]),
+    "koe_dual_stream_ring": (C.c_int, [C.POINTER(CoreWeightsStruct), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "koe_logmel_normalise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "koe_emotion_stream": (C.c_int, [C.POINTER(CoreWeightsStruct), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

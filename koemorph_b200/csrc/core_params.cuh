@@ -17,6 +17,8 @@ struct CoreParams {
   const float* mel_long;
   const float* mel_short;
   int n_long;
+  // ring mode (koe_dual_stream_ring): plain and lo-edge rows are slots of per-stream rings, the hi-edge row is per stream
+  int ring_frames, ring_base;
 };
 
 // frame k of window wi of clip b: which buffer and which row (see koe_dual_stream_windows in the header)
@@ -26,6 +28,8 @@ __device__ __forceinline__ int window_variant(const CoreParams& p, int k) {
   return 0;
 }
 __device__ __forceinline__ long long window_row(const CoreParams& p, int variant, int b, int wi, int k) {
+  if (p.ring_frames > 0)
+    return variant == 2 ? (long long)b : (long long)b * p.ring_frames + (p.ring_base + k) % p.ring_frames;
   return variant == 0 ? (long long)b * p.n_frames + (long long)wi * p.stride_frames + k
                       : (long long)b * p.n_out + wi;
 }

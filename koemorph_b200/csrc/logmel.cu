@@ -49,9 +49,12 @@ struct LogmelParams {
   int64_t audio_stride;
   int n_clips, n_samples, hop, n_frames;
   int lo_rel, hi_rel;
-  int frame_offset, frame_step;  // output row j is the frame centred on (frame_offset + j*frame_step)*hop
+  int frame_offset, frame_step;  // output row j is the frame centred on sample_offset + (frame_offset + j*frame_step)*hop
+  int sample_offset;
+  int pad_mode;                  // 0: samples outside the clip are zero; 1: reflected (numpy "reflect")
   float* power;
   float* frame_max;
+  long long power_clip_stride, fmax_clip_stride;  // elements between consecutive clips' output blocks
 };
 
 __host__ __device__ constexpr int bitrev5(int i) {
@@ -161,19 +164,19 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
       const int fa = p.frame_offset + ga * p.frame_step, fb = fa + p.frame_step;  // frame indices in hops
       int lo_a = 0, hi_a = p.n_samples, lo_b = 0, hi_b = p.n_samples;
       if (p.lo_rel != KOE_NO_EDGE) {
-        lo_a = max(lo_a, (fa + p.lo_rel) * p.hop);
-        lo_b = max(lo_b, (fb + p.lo_rel) * p.hop);
+        lo_a = max(lo_a, p.sample_offset + (fa + p.lo_rel) * p.hop);
+        lo_b = max(lo_b, p.sample_offset + (fb + p.lo_rel) * p.hop);
       }
       if (p.hi_rel != KOE_NO_EDGE) {
-        hi_a = min(hi_a, (fa + p.hi_rel) * p.hop);
-        hi_b = min(hi_b, (fb + p.hi_rel) * p.hop);
+        hi_a = min(hi_a, p.sample_offset + (fa + p.hi_rel) * p.hop);
+        hi_b = min(hi_b, p.sample_offset + (fb + p.hi_rel) * p.hop);
       }
       if (!has_b) hi_b = lo_b;  // empty range: second frame reads as silence
-      const int sa0 = fa * p.hop - kFrameLen / 2 + lane;
-      const int sb0 = fb * p.hop - kFrameLen / 2 + lane;
+      const int fa_lo = p.sample_offset + fa * p.hop - kFrameLen / 2;  // first sample of each frame
+      const int fb_lo = p.sample_offset + fb * p.hop - kFrameLen / 2;
+      const int sa0 = fa_lo + lane, sb0 = fb_lo + lane;
 
       float re[32], im[32];
-      const int fa_lo = fa * p.hop - kFrameLen / 2, fb_lo = fb * p.hop - kFrameLen / 2;
       if (fa_lo >= lo_a && fa_lo + kFrameLen <= hi_a && fb_lo >= lo_b && fb_lo + kFrameLen <= hi_b) {
         // interior frames (all but the first / last of a clip): no masking, one base pointer per frame
         const float* __restrict__ pa = clip + sa0;
@@ -183,6 +186,20 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
           const float w = s_hann[32 * n1 + lane];
           re[n1] = __ldg(pa + 32 * n1) * w;
           im[n1] = __ldg(pb + 32 * n1) * w;
+        }
+      } else if (p.pad_mode == 1) {
+        // numpy "reflect" padding about the first / last sample (MelSlidingWindowExtractor default)
+        const int last = p.n_samples - 1;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          int sa = sa0 + 32 * n1, sb = sb0 + 32 * n1;
+          sa = sa < 0 ? -sa : (sa > last ? 2 * last - sa : sa);
+          sb = sb < 0 ? -sb : (sb > last ? 2 * last - sb : sb);
+          const float w = s_hann[32 * n1 + lane];
+          const float va = (sa >= 0 && sa <= last) ? __ldg(clip + sa) : 0.0f;
+          const float vb = (has_b && sb >= 0 && sb <= last) ? __ldg(clip + sb) : 0.0f;
+          re[n1] = va * w;
+          im[n1] = vb * w;
         }
       } else {
 #pragma unroll
@@ -296,7 +313,7 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
           const int g = 2 * (int)(pr_ % ppc) + h;
           if (g < p.n_frames) {
             const float* trow = s_tile + (2 * warp + h) * kTileStride;
-            float* dst = p.power + ((long long)b * p.n_frames + g) * KOE_N_MELS;
+            float* dst = p.power + (long long)b * p.power_clip_stride + (long long)g * KOE_N_MELS;
             // stored in dB: 10 log10(max(power, amin)); the consumer only subtracts its reference and clamps
             const float v0 = power_db(trow[lane]), v1 = power_db(trow[lane + 32]);
             const float v2 = lane < 16 ? power_db(trow[lane + 64]) : -INFINITY;
@@ -304,7 +321,7 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
             dst[lane + 32] = v1;
             if (lane < 16) dst[lane + 64] = v2;
             const float mx = warp_max(fmaxf(fmaxf(v0, v1), v2));
-            if (lane == 0 && p.frame_max != nullptr) p.frame_max[(long long)b * p.n_frames + g] = mx;
+            if (lane == 0 && p.frame_max != nullptr) p.frame_max[(long long)b * p.fmax_clip_stride + g] = mx;
           }
         }
       }
@@ -527,18 +544,26 @@ extern "C" int koe_frontend_filterbank_host(const koe_frontend_t* fe, float* fb_
   return KOE_OK;
 }
 
-extern "C" int koe_logmel_power(const koe_frontend_t* fe, const float* audio, int64_t audio_stride, int n_clips,
-                                int n_samples, int hop, int n_frames, int frame_offset, int frame_step,
-                                int lo_rel_hops, int hi_rel_hops, float* power, float* frame_max, void* stream) {
-  KOE_REQUIRE(fe != nullptr && audio != nullptr && power != nullptr, "koe_logmel_power: NULL argument");
-  KOE_REQUIRE(n_clips >= 0 && n_samples >= 0 && n_frames >= 0, "koe_logmel_power: negative size");
-  KOE_REQUIRE(hop > 0 && audio_stride >= n_samples, "koe_logmel_power: bad hop/stride");
-  KOE_REQUIRE(frame_offset >= 0 && frame_step >= 1, "koe_logmel_power: bad frame_offset/frame_step");
-  KOE_REQUIRE(((long long)frame_offset + (long long)(n_frames + 1) * frame_step + KOE_MAX_EDGE + 1) * hop < (1ll << 31) &&
-                  n_samples < (1 << 30),
+extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_args* a, void* stream) {
+  KOE_REQUIRE(fe != nullptr && a != nullptr && a->audio != nullptr && a->power != nullptr,
+              "koe_logmel_power: NULL argument");
+  KOE_REQUIRE(a->n_clips >= 0 && a->n_samples >= 0 && a->n_frames >= 0, "koe_logmel_power: negative size");
+  KOE_REQUIRE(a->hop > 0 && a->audio_stride >= a->n_samples, "koe_logmel_power: bad hop/stride");
+  KOE_REQUIRE(a->frame_offset >= 0 && a->frame_step >= 1 && a->sample_offset >= 0,
+              "koe_logmel_power: bad frame_offset/frame_step/sample_offset");
+  KOE_REQUIRE((long long)a->sample_offset +
+                      ((long long)a->frame_offset + (long long)(a->n_frames + 1) * a->frame_step + KOE_MAX_EDGE + 1) *
+                          a->hop < (1ll << 31) && a->n_samples < (1 << 30),
               "koe_logmel_power: clip too long for 32-bit sample indices");
-  KOE_REQUIRE((reinterpret_cast<uintptr_t>(power) & 15) == 0, "koe_logmel_power: power must be 16-byte aligned");
-  if (n_clips == 0 || n_frames == 0) return KOE_OK;
+  KOE_REQUIRE(a->pad_mode == 0 || a->pad_mode == 1, "koe_logmel_power: pad_mode must be 0 (constant) or 1 (reflect)");
+  KOE_REQUIRE(a->pad_mode == 0 || (a->lo_rel_hops == KOE_NO_EDGE && a->hi_rel_hops == KOE_NO_EDGE &&
+                                   a->n_samples > KOE_N_FFT / 2),
+              "koe_logmel_power: reflect padding needs n_samples > n_fft/2 and no window edges");
+  KOE_REQUIRE(a->power_clip_stride >= (int64_t)a->n_frames * KOE_N_MELS && a->power_clip_stride % 4 == 0,
+              "koe_logmel_power: bad power_clip_stride");
+  KOE_REQUIRE(a->frame_max == nullptr || a->frame_max_clip_stride >= a->n_frames,
+              "koe_logmel_power: bad frame_max_clip_stride");
+  if (a->n_clips == 0 || a->n_frames == 0) return KOE_OK;
   FrontendTables tab;
   tab.hann = fe->d_hann;
   tab.tw = fe->d_tw;
@@ -547,26 +572,53 @@ extern "C" int koe_logmel_power(const koe_frontend_t* fe, const float* audio, in
   tab.runs = fe->d_tables + kMaxBins;
   tab.n_bins = fe->n_bins;
   LogmelParams p;
-  p.audio = audio;
-  p.audio_stride = audio_stride;
-  p.n_clips = n_clips;
-  p.n_samples = n_samples;
-  p.hop = hop;
-  p.n_frames = n_frames;
-  p.lo_rel = lo_rel_hops;
-  p.hi_rel = hi_rel_hops;
-  p.frame_offset = frame_offset;
-  p.frame_step = frame_step;
-  p.power = power;
-  p.frame_max = frame_max;
-  const long long ppc = (n_frames + 1) / 2;
-  const long long n_blocks = ((long long)n_clips * ppc + kWarps - 1) / kWarps;
+  p.audio = a->audio;
+  p.audio_stride = a->audio_stride;
+  p.n_clips = a->n_clips;
+  p.n_samples = a->n_samples;
+  p.hop = a->hop;
+  p.n_frames = a->n_frames;
+  p.lo_rel = a->lo_rel_hops;
+  p.hi_rel = a->hi_rel_hops;
+  p.frame_offset = a->frame_offset;
+  p.frame_step = a->frame_step;
+  p.sample_offset = a->sample_offset;
+  p.pad_mode = a->pad_mode;
+  p.power = a->power;
+  p.frame_max = a->frame_max;
+  p.power_clip_stride = a->power_clip_stride;
+  p.fmax_clip_stride = a->frame_max_clip_stride;
+  const long long ppc = (a->n_frames + 1) / 2;
+  const long long n_blocks = ((long long)a->n_clips * ppc + kWarps - 1) / kWarps;
   const long long max_grid = (long long)fe->num_sms * fe->occupancy;
   const int grid = (int)std::min(n_blocks, max_grid);
   logmel_power_kernel<<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
   count_launch();
   KOE_CUDA(cudaGetLastError());
   return KOE_OK;
+}
+
+extern "C" int koe_logmel_power(const koe_frontend_t* fe, const float* audio, int64_t audio_stride, int n_clips,
+                                int n_samples, int hop, int n_frames, int frame_offset, int frame_step,
+                                int lo_rel_hops, int hi_rel_hops, float* power, float* frame_max, void* stream) {
+  koe_logmel_args a;
+  a.audio = audio;
+  a.audio_stride = audio_stride;
+  a.n_clips = n_clips;
+  a.n_samples = n_samples;
+  a.hop = hop;
+  a.n_frames = n_frames;
+  a.frame_offset = frame_offset;
+  a.frame_step = frame_step;
+  a.sample_offset = 0;
+  a.lo_rel_hops = lo_rel_hops;
+  a.hi_rel_hops = hi_rel_hops;
+  a.pad_mode = 0;
+  a.power = power;
+  a.power_clip_stride = (int64_t)n_frames * KOE_N_MELS;
+  a.frame_max = frame_max;
+  a.frame_max_clip_stride = n_frames;
+  return koe_logmel_power_ex(fe, &a, stream);
 }
 
 extern "C" int koe_logmel_normalise(const float* power, const float* frame_max, int n_clips, int n_frames,

@@ -60,23 +60,41 @@ class LogMelFrontend:
 
     def power(self, audio: torch.Tensor, hop: int, n_frames: int, frame_offset: int = 0, frame_step: int = 1,
               lo_rel: Optional[int] = None, hi_rel: Optional[int] = None,
-              out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+              out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, sample_offset: int = 0,
+              pad_mode: str = "constant", out_row: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         """audio (B, L) float32 CUDA -> mel power in dB, 10*log10(max(p, 1e-10)), (B, n_frames, 80) and its
-        per-frame max (B, n_frames)."""
+        per-frame max (B, n_frames).
+
+        With ``out=(power, fmax)`` of shapes (B, R, 80) / (B, R) the n_frames rows are written at rows
+        ``out_row ...`` of every clip's block (ring buffers of the streaming paths)."""
         audio = _lib.require_cuda(audio, "audio")
         if audio.dim() != 2:
             raise ValueError(f"audio must be (B, L), got {tuple(audio.shape)}")
+        if pad_mode not in ("constant", "reflect"):
+            raise ValueError(f"pad_mode must be 'constant' or 'reflect', got {pad_mode!r}")
         B, L = audio.shape
         if out is None:
             power = torch.empty((B, n_frames, self.n_mels), dtype=torch.float32, device=audio.device)
             fmax = torch.empty((B, n_frames), dtype=torch.float32, device=audio.device)
         else:
             power, fmax = out
+            if power.shape[0] != B or power.shape[2] != self.n_mels or out_row + n_frames > power.shape[1] or \
+                    fmax.shape[:2] != power.shape[:2] or not power.is_contiguous() or not fmax.is_contiguous():
+                raise ValueError("out must be contiguous (B, R, 80) / (B, R) tensors with out_row + n_frames <= R")
+        a = _lib.LogmelArgs()
+        a.audio, a.audio_stride = audio.data_ptr(), audio.stride(0)
+        a.n_clips, a.n_samples, a.hop, a.n_frames = B, L, hop, n_frames
+        a.frame_offset, a.frame_step, a.sample_offset = frame_offset, frame_step, sample_offset
+        a.lo_rel_hops = _lib.KOE_NO_EDGE if lo_rel is None else lo_rel
+        a.hi_rel_hops = _lib.KOE_NO_EDGE if hi_rel is None else hi_rel
+        a.pad_mode = 1 if pad_mode == "reflect" else 0
+        a.power = power.data_ptr() + out_row * self.n_mels * 4
+        a.power_clip_stride = power.stride(0)
+        a.frame_max = fmax.data_ptr() + out_row * 4
+        a.frame_max_clip_stride = fmax.stride(0)
         with torch.cuda.device(audio.device):
-            _lib.check(self._lib.koe_logmel_power(
-                self._h, audio.data_ptr(), audio.stride(0), B, L, hop, n_frames, frame_offset, frame_step,
-                _lib.KOE_NO_EDGE if lo_rel is None else lo_rel, _lib.KOE_NO_EDGE if hi_rel is None else hi_rel,
-                power.data_ptr(), fmax.data_ptr(), _lib.stream_ptr(audio.device)), "koe_logmel_power")
+            _lib.check(self._lib.koe_logmel_power_ex(self._h, C.byref(a), _lib.stream_ptr(audio.device)),
+                       "koe_logmel_power")
         return power, fmax
 
     def normalise(self, power: torch.Tensor, fmax: torch.Tensor, db_only: bool = False):
