@@ -19,6 +19,7 @@ struct CoreParams {
   int n_long;
   // ring mode (koe_dual_stream_ring): plain and lo-edge rows are slots of per-stream rings, the hi-edge row is per stream
   int ring_frames, ring_base;
+  long long* dbg;  // optional phase timestamps of CTA 0 (bring-up / profiling only), NULL in production
 };
 
 // frame k of window wi of clip b: which buffer and which row (see koe_dual_stream_windows in the header)

@@ -320,90 +320,150 @@ __global__ void __launch_bounds__(kCoreThreads, 1) dual_stream_fp32_kernel(CoreP
   }
 }
 
-// ---- emotion stream: 8 clips per CTA --------------------------------------------------------------
-constexpr int kEmoClips = 8;
+// ---- emotion stream: 16 clips per CTA, weights streamed through shared memory in 64-row cp.async chunks ----------
+constexpr int kEmoClips = 16;
 constexpr int kEmoInMax = 272;
+constexpr int kEmoChunkRows = 64;
+constexpr int kEmoBufFloats = kEmoChunkRows * kD;   // one chunk buffer: 64 rows of up to 256 floats (64 KB)
+constexpr size_t kEmoSmem = sizeof(float) * (2 * kEmoBufFloats + kEmoInMax * kEmoClips + kD * kEmoClips + 16 * 8 + 32);
 
 __global__ void __launch_bounds__(256) emotion_stream_kernel(koe_core_weights W, const float* __restrict__ emo_in,
                                                              int n_clips, float* __restrict__ expr_sigmoid) {
-  __shared__ float s_x[kEmoClips][kEmoInMax];
-  __shared__ float s_z[kEmoClips][kD];
-  __shared__ float s_red[kEmoClips][8];
-  __shared__ float s_stat[kEmoClips][2];
+  extern __shared__ __align__(16) float esm[];
+  float* s_buf = esm;                                   // [2][64][<=256]
+  float* s_x = s_buf + 2 * kEmoBufFloats;               // [emo_in][16]  (clip-contiguous: broadcast float4 loads)
+  float* s_z = s_x + kEmoInMax * kEmoClips;             // [256][16]
+  float* s_red = s_z + kD * kEmoClips;                  // [16][8]
+  float* s_stat = s_red + 16 * 8;                       // [16][2]
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int c0 = blockIdx.x * kEmoClips;
   const int nc = min(kEmoClips, n_clips - c0);
+  const int n1 = (W.emo_in + kEmoChunkRows - 1) / kEmoChunkRows;   // chunks of we1_t [emo_in][256]
+  const int n2 = kD / kEmoChunkRows;                               // chunks of we2_t [256][128]
+
+  auto issue = [&](int c) {  // chunk c of the concatenated chunk sequence -> buffer c & 1
+    const float* src;
+    int floats;
+    if (c < n1) {
+      const int r0 = c * kEmoChunkRows;
+      src = W.we1_t + (size_t)r0 * kD;
+      floats = min(kEmoChunkRows, W.emo_in - r0) * kD;
+    } else {
+      src = W.we2_t + (size_t)(c - n1) * kEmoChunkRows * 128;
+      floats = kEmoChunkRows * 128;
+    }
+    float* dst = s_buf + (c & 1) * kEmoBufFloats;
+    for (int i = tid; i < floats / 4; i += 256) cp_async16(dst + 4 * i, src + 4 * i);
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
   for (int i = tid; i < kEmoClips * W.emo_in; i += 256) {
     const int c = i / W.emo_in, k = i % W.emo_in;
-    s_x[c][k] = c < nc ? emo_in[(size_t)(c0 + c) * W.emo_in + k] : 0.0f;
+    s_x[k * kEmoClips + c] = c < nc ? emo_in[(size_t)(c0 + c) * W.emo_in + k] : 0.0f;
   }
-  __syncthreads();
-  // z[c][n] = we1_t[:, n] . x[c] + be1[n]   (thread = feature n)
+
+  // ---- z[c][n] = we1_t[:, n] . x[c] + be1[n]   (thread = feature n, 16 clips in registers)
   float z[kEmoClips];
   {
     const float b = __ldg(W.be1 + tid);
 #pragma unroll
     for (int c = 0; c < kEmoClips; ++c) z[c] = b;
-    for (int k = 0; k < W.emo_in; ++k) {
-      const float w = __ldg(W.we1_t + (size_t)k * kD + tid);
+  }
+  int chunk = 0;
+  for (; chunk < n1; ++chunk) {
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* wb = s_buf + (chunk & 1) * kEmoBufFloats + tid;
+    const int r0 = chunk * kEmoChunkRows, rows = min(kEmoChunkRows, W.emo_in - r0);
+#pragma unroll 4
+    for (int k = 0; k < rows; ++k) {
+      const float w = wb[k * kD];
+      const float4* xr = reinterpret_cast<const float4*>(s_x + (r0 + k) * kEmoClips);
 #pragma unroll
-      for (int c = 0; c < kEmoClips; ++c) z[c] = fmaf(w, s_x[c][k], z[c]);
+      for (int q = 0; q < 4; ++q) {
+        const float4 x = xr[q];
+        z[4 * q + 0] = fmaf(w, x.x, z[4 * q + 0]);
+        z[4 * q + 1] = fmaf(w, x.y, z[4 * q + 1]);
+        z[4 * q + 2] = fmaf(w, x.z, z[4 * q + 2]);
+        z[4 * q + 3] = fmaf(w, x.w, z[4 * q + 3]);
+      }
     }
+    __syncthreads();
+    if (chunk + 2 < n1 + n2) issue(chunk + 2); else cp_async_commit();
   }
-  // LayerNorm per clip over the 256 threads
+  // ---- LayerNorm per clip over the 256 threads (two passes)
 #pragma unroll
   for (int c = 0; c < kEmoClips; ++c) {
-    const float s = warp_sum(z[c]);
-    if (tx == 0) s_red[c][ty] = s;
+    const float v = warp_sum(z[c]);
+    if (tx == 0) s_red[c * 8 + ty] = v;
   }
   __syncthreads();
   if (tid < kEmoClips) {
-    float s = 0.0f;
-    for (int w = 0; w < 8; ++w) s += s_red[tid][w];
-    s_stat[tid][0] = s * (1.0f / kD);
+    float v = 0.0f;
+    for (int w = 0; w < 8; ++w) v += s_red[tid * 8 + w];
+    s_stat[tid * 2] = v * (1.0f / kD);
   }
   __syncthreads();
 #pragma unroll
   for (int c = 0; c < kEmoClips; ++c) {
-    const float d = z[c] - s_stat[c][0];
-    const float s = warp_sum(d * d);
-    if (tx == 0) s_red[c][ty] = s;
+    const float d = z[c] - s_stat[c * 2];
+    const float v = warp_sum(d * d);
+    if (tx == 0) s_red[c * 8 + ty] = v;
   }
   __syncthreads();
   if (tid < kEmoClips) {
-    float s = 0.0f;
-    for (int w = 0; w < 8; ++w) s += s_red[tid][w];
-    s_stat[tid][1] = rsqrtf(s * (1.0f / kD) + W.ln_eps);
+    float v = 0.0f;
+    for (int w = 0; w < 8; ++w) v += s_red[tid * 8 + w];
+    s_stat[tid * 2 + 1] = rsqrtf(v * (1.0f / kD) + W.ln_eps);
   }
   __syncthreads();
   {
     const float g = __ldg(W.eln_g + tid), be = __ldg(W.eln_b + tid);
 #pragma unroll
-    for (int c = 0; c < kEmoClips; ++c) s_z[c][tid] = (z[c] - s_stat[c][0]) * s_stat[c][1] * g + be;
+    for (int c = 0; c < kEmoClips; ++c)
+      s_z[tid * kEmoClips + c] = (z[c] - s_stat[c * 2]) * s_stat[c * 2 + 1] * g + be;
   }
-  __syncthreads();
-  // h[c][j] = relu(we2_t[:, j] . zn[c] + be2[j]); thread = (j = tid & 127, clip half = tid >> 7)
+  // ---- h[c][j] = relu(we2_t[:, j] . zn[c] + be2[j]); thread = (j = tid & 127, clip half = tid >> 7)
+  const int j = tid & 127, half = tid >> 7;
+  float h[kEmoClips / 2];
   {
-    const int j = tid & 127, half = tid >> 7;
-    float h[kEmoClips / 2];
     const float b = __ldg(W.be2 + j);
 #pragma unroll
     for (int c = 0; c < kEmoClips / 2; ++c) h[c] = b;
-    for (int n = 0; n < kD; ++n) {
-      const float w = __ldg(W.we2_t + (size_t)n * 128 + j);
+  }
+  for (; chunk < n1 + n2; ++chunk) {
+    cp_async_wait<1>();
+    __syncthreads();   // also orders the s_z writes above before the first read
+    const float* wb = s_buf + (chunk & 1) * kEmoBufFloats + j;
+    const int r0 = (chunk - n1) * kEmoChunkRows;
+#pragma unroll 4
+    for (int k = 0; k < kEmoChunkRows; ++k) {
+      const float w = wb[k * 128];
+      const float4* zr = reinterpret_cast<const float4*>(s_z + (r0 + k) * kEmoClips + half * (kEmoClips / 2));
 #pragma unroll
-      for (int c = 0; c < kEmoClips / 2; ++c) h[c] = fmaf(w, s_z[half * (kEmoClips / 2) + c][n], h[c]);
+      for (int q = 0; q < 2; ++q) {
+        const float4 x = zr[q];
+        h[4 * q + 0] = fmaf(w, x.x, h[4 * q + 0]);
+        h[4 * q + 1] = fmaf(w, x.y, h[4 * q + 1]);
+        h[4 * q + 2] = fmaf(w, x.z, h[4 * q + 2]);
+        h[4 * q + 3] = fmaf(w, x.w, h[4 * q + 3]);
+      }
     }
+    __syncthreads();
+    if (chunk + 2 < n1 + n2) issue(chunk + 2); else cp_async_commit();
+  }
+  {
     const float w2 = __ldg(W.w2 + j);
 #pragma unroll
     for (int c = 0; c < kEmoClips / 2; ++c) {
-      const float s = warp_sum(fmaxf(h[c], 0.0f) * w2);
-      if (tx == 0) s_red[half * (kEmoClips / 2) + c][ty & 3] = s;
+      const float v = warp_sum(fmaxf(h[c], 0.0f) * w2);
+      if (tx == 0) s_red[(half * (kEmoClips / 2) + c) * 8 + (ty & 3)] = v;
     }
   }
   __syncthreads();
   if (tid < nc) {
-    const float logit = s_red[tid][0] + s_red[tid][1] + s_red[tid][2] + s_red[tid][3] + W.b2;
+    const float logit = s_red[tid * 8] + s_red[tid * 8 + 1] + s_red[tid * 8 + 2] + s_red[tid * 8 + 3] + W.b2;
     expr_sigmoid[c0 + tid] = 1.0f / (1.0f + expf(-logit));
   }
 }
@@ -493,13 +553,26 @@ extern "C" int koe_emotion_stream(const koe_core_weights* w, const float* emo_in
   KOE_REQUIRE(emo_in != nullptr && expr_sigmoid != nullptr && n_clips >= 0, "koe_emotion_stream: bad argument");
   if (n_clips == 0) return KOE_OK;
   const int grid = (n_clips + kEmoClips - 1) / kEmoClips;
-  emotion_stream_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
+  static bool configured[64] = {false};
+  int dev = 0;
+  KOE_CUDA(cudaGetDevice(&dev));
+  KOE_REQUIRE(dev >= 0 && dev < 64, "device index too large");
+  if (!configured[dev]) {
+    KOE_CUDA(cudaFuncSetAttribute(emotion_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmoSmem));
+    configured[dev] = true;
+  }
+  emotion_stream_kernel<<<grid, 256, kEmoSmem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
   count_launch();
   KOE_CUDA(cudaGetLastError());
   return KOE_OK;
 }
 
-static int launch_core(const CoreParams& p, int precision, cudaStream_t stream) {
+static long long* g_tc_debug = nullptr;
+extern "C" void koe_debug_set_tc_timestamps(long long* device_buffer_128) { g_tc_debug = device_buffer_128; }
+
+static int launch_core(const CoreParams& p_in, int precision, cudaStream_t stream) {
+  CoreParams p = p_in;
+  p.dbg = g_tc_debug;
   if (precision == 0) {
     static int num_sms[64] = {0};
     int dev = 0;

@@ -26,8 +26,8 @@ namespace koe {
 
 namespace tc {
 
-constexpr int kThreads = 192;
-constexpr int kSimt = 128;
+constexpr int kThreads = 320;   // warps 0-7 SIMT (two warpgroups), warp 8 TMA producer, warp 9 MMA issuer
+constexpr int kSimt = 256;
 constexpr int kStageBytes = 16384;
 constexpr int kRing = 4;
 constexpr int kTok = 80;
@@ -39,12 +39,14 @@ constexpr int kESbo = 32 * 128;                   // enc / Oflat: K = 256 -> 32 
 constexpr int kPSbo = 10 * 128;                   // P / vT tiles: K = 80 -> 10 chunks
 constexpr int kPTile = 16 * kPSbo;                // 20480
 constexpr int kStagesG1 = 9, kStagesTile = 4;
-constexpr int kStagesPerWindow = kStagesG1 + 5 * kStagesTile;  // 29
+constexpr int kStagesPerWindow = kStagesG1 + 5 * kStagesTile;  // 29 weight stages
+constexpr int kMelRows = 48;                      // mel rows (frames) per ring stage: 48 * 320 B = 15360 B, 6 K-chunks
+constexpr int kMelStageBytes = kMelRows * kTok * 4;
 
 // shared memory map (bytes)
 constexpr int kOffBar = 0;                        // mbarriers + tmem base
-constexpr int kOffConst = 256;                    // bc, ln_g, ln_b, bv (256 each), ba, w2 (128 each)
-constexpr int kOffX = kOffConst + 1280 * 4;       // A1 (43520) / P tiles (40960)
+constexpr int kOffConst = 256;                    // bc, ln_g, ln_b, bv (256 each), ba, w2 (128 each), LN partials (512)
+constexpr int kOffX = kOffConst + 1792 * 4;       // A1 (43520) / P tiles (40960)
 constexpr int kOffE = kOffX + 10 * kA1Sbo;        // enc (40960) / Oflat
 constexpr int kOffVT = kOffE + 10 * kESbo;        // vT tiles (40960)
 constexpr int kOffRing = kOffVT + 2 * kPTile;
@@ -151,7 +153,11 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   return o;
 }
 
-__device__ __forceinline__ void simt_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void stamp(long long* dbg, int slot) {
+  if (dbg != nullptr) dbg[slot] = clock64();
+}
+
+__device__ __forceinline__ void simt_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -167,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   float* s_const = reinterpret_cast<float*>(smem + kOffConst);
   const float *s_bc = s_const, *s_g = s_const + 256, *s_b = s_const + 512, *s_bv = s_const + 768;
   const float *s_ba = s_const + 1024, *s_w2 = s_const + 1152;
+  float* s_ln = s_const + 1280;  // [stat 2][warpgroup 2][row 128]
 
   if (tid == 0) {
     for (int i = 0; i < kRing; ++i) {
@@ -184,13 +191,15 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       s_const[512 + i] = W.ln_b[i];
       s_const[768 + i] = W.bv[i];
     }
-    s_const[1024 + tid] = W.ba[tid];
-    s_const[1152 + tid] = W.w2[tid];
+    if (tid < 128) {
+      s_const[1024 + tid] = W.ba[tid];
+      s_const[1152 + tid] = W.w2[tid];
+    }
     // operand regions start as zeros so that never-written rows / K tails are finite
     uint4* z = reinterpret_cast<uint4*>(smem + kOffX);
     for (int i = tid; i < (kOffRing - kOffX) / 16; i += kSimt) z[i] = make_uint4(0, 0, 0, 0);
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
         smem_u32((const void*)s_tmem)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -203,13 +212,32 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
 
   const int n_items = p.n_clips * p.n_out;
   const int T = p.frames_per_window;
+  // plain linear layout (not prenormalised features, not the streaming rings): mel rows arrive by TMA
+  const bool tma_mel = p.mel_long == nullptr && p.ring_frames == 0;
+  const int Tl = min(T, p.mel_seq);                              // long-term frames actually present
+  const int n_mel_stages = tma_mel ? (Tl + kMelRows - 1) / kMelRows : 0;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // =========================================================== TMA producer ==========================
     if (lane == 0) {
       const unsigned char* src = reinterpret_cast<const unsigned char*>(W.tc_bf16);
       uint32_t slot = 0, phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        if (tma_mel) {
+          // the window's plain mel rows [0, Tl) are contiguous in HBM: stream them through the same ring, ahead of the
+          // weights, so that by the time the SIMT warps start a window its rows are already in shared memory
+          const int b = item / p.n_out, wi = item % p.n_out;
+          const unsigned char* rows =
+              reinterpret_cast<const unsigned char*>(p.power[0] + window_row(p, 0, b, wi, 0) * kTok);
+          for (int s = 0; s < n_mel_stages; ++s) {
+            const uint32_t bytes = (uint32_t)min(kMelRows, Tl - kMelRows * s) * kTok * 4;
+            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+            mbar_expect_tx(bar_full + 8 * slot, bytes);
+            bulk_g2s(sbase + kOffRing + slot * kStageBytes, rows + (size_t)s * kMelStageBytes, bytes,
+                     bar_full + 8 * slot);
+            if (++slot == kRing) slot = 0, phase ^= 1;
+          }
+        }
         for (int s = 0; s < kStagesPerWindow; ++s) {
           mbar_wait(bar_empty + 8 * slot, phase ^ 1);
           mbar_expect_tx(bar_full + 8 * slot, kStageBytes);
@@ -219,14 +247,18 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // =========================================================== MMA issuer ============================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0, go_phase = 0;
       const uint32_t ring = sbase + kOffRing;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        long long* dm = (p.dbg != nullptr && blockIdx.x == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 64 + 16 * (item / gridDim.x) : nullptr;
+        for (int s = 0; s < n_mel_stages; ++s)  // ring slots consumed by the SIMT warps
+          if (++slot == kRing) slot = 0, phase ^= 1;
         // ---- G1: 9 stages of [256 x 32] weights; the last stage carries K = 256..271 only
         mbar_wait(bar_go, go_phase), go_phase ^= 1;
+        stamp(dm, 0);
         tc_fence_after();
         for (int s = 0; s < kStagesG1; ++s) {
           mbar_wait(bar_full + 8 * slot, phase);
@@ -241,8 +273,10 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           if (++slot == kRing) slot = 0, phase ^= 1;
         }
         tc_commit(bar_done);
+        stamp(dm, 1);
         // ---- S (2 tiles) and VT (2 tiles): A = weight stage [128 x 64], B = enc [80 x 256]
         mbar_wait(bar_go, go_phase), go_phase ^= 1;
+        stamp(dm, 2);
         tc_fence_after();
         for (int tile = 0; tile < 4; ++tile) {
           const uint32_t d = tmem + (tile < 2 ? kColS + 80 * tile : kColVT + 80 * (tile - 2));
@@ -259,8 +293,10 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           }
         }
         tc_commit(bar_done);
+        stamp(dm, 3);
         // ---- PV: A = P tile [128 x 80], B = vT tile [128 x 80]
         mbar_wait(bar_go, go_phase), go_phase ^= 1;
+        stamp(dm, 4);
         tc_fence_after();
         for (int t = 0; t < 2; ++t)
           for (int j = 0; j < 5; ++j) {
@@ -269,8 +305,10 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
             tc_mma_bf16(tmem + kColO + 128 * t, a, b, idesc_bf16(128, 128), j != 0);
           }
         tc_commit(bar_done);
+        stamp(dm, 5);
         // ---- H1: A = Oflat [128(28) x 256], B = weight stage [128 x 64]
         mbar_wait(bar_go, go_phase), go_phase ^= 1;
+        stamp(dm, 6);
         tc_fence_after();
         for (int s = 0; s < kStagesTile; ++s) {
           mbar_wait(bar_full + 8 * slot, phase);
@@ -284,15 +322,22 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           if (++slot == kRing) slot = 0, phase ^= 1;
         }
         tc_commit(bar_done);
+        stamp(dm, 7);
       }
     }
   } else {
-    // =========================================================== SIMT warps 0-3 ========================
-    uint32_t done_phase = 0;
-    const uint32_t lane_taddr = tmem + ((uint32_t)(32 * warp) << 16);  // this warp's TMEM lane quarter
+    // =========================================================== SIMT warps 0-7 ========================
+    // warpgroup wg = warp / 4; warps w and w + 4 both own TMEM lanes 32 (w % 4) .. +31, so the two warpgroups split
+    // every epilogue between them (LayerNorm: column halves; softmax / vT / O: one tile of 4 heads each)
+    uint32_t done_phase = 0, slot = 0, phase = 0;
+    const int wg = warp >> 2, wq = warp & 3;
+    const int row = 32 * wq + lane;                                        // TMEM lane == accumulator row
+    const uint32_t lane_taddr = tmem + ((uint32_t)(32 * wq) << 16);
     const bool prenorm = p.mel_long != nullptr;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.n_out, wi = item % p.n_out;
+      long long* ds = (p.dbg != nullptr && blockIdx.x == 0 && tid == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 16 * (item / gridDim.x) : nullptr;
+      stamp(ds, 0);
       // ---- window dB reference
       float ref_db = 0.0f;
       if (!prenorm) {
@@ -304,125 +349,198 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         mx = warp_max(mx);
         if (lane == 0) s_red[warp] = mx;
         simt_barrier();
-        ref_db = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+        ref_db = fmaxf(fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3])),
+                       fmaxf(fmaxf(s_red[4], s_red[5]), fmaxf(s_red[6], s_red[7])));
         simt_barrier();
       }
-      // ---- A1: Xn[channel j][time t] as bf16.  One item = 8 consecutive frames x 4 consecutive channels:
-      // 8 independent 16-byte loads (frame rows are 320 B apart), then one 16-byte store per channel.
-      // Two items are in flight per thread so that ~32 KB of loads per CTA hide the L2 latency.
-      {
-        constexpr int kQuads = kTok / 4;                 // 20 channel quads per frame
-        constexpr int kItems = kA1Chunks * kQuads;       // 680
-        auto load_item = [&](int idx, float4 (&r)[8]) {
-          const int c = idx / kQuads, q = idx % kQuads;
+      if (tma_mel) {
+        // ---- A1 from the TMA-staged rows: Xn[channel j][time t] as bf16, one 16-byte store = 8 frames of a channel
+        // rows that are not plain frames of this window (short-term detail, edge variants) are fetched directly, early
+        float extra[4] = {0.f, 0.f, 0.f, 0.f};            // [0..2] short-term frames T-3+s, [3] lo-edge frame 0
+        if (tid < kTok) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int t = 8 * c + e;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t < kKMel) {
-              if (prenorm) {
-                if (t >= p.mel_seq)
-                  x = __ldg(reinterpret_cast<const float4*>(p.mel_short + ((size_t)b * 3 + (t - p.mel_seq)) * kTok) + q);
-                else if (t < p.n_long)
-                  x = __ldg(reinterpret_cast<const float4*>(p.mel_long + ((size_t)b * p.n_frames + t) * kTok) + q);
-              } else {
-                int k;
-                if (t < p.mel_seq)
-                  k = t < T ? t : -1;
-                else {
-                  const int s = t - p.mel_seq;
-                  k = T >= 3 ? T - 3 + s : (s < T ? s : -1);
-                }
-                if (k >= 0) {
-                  const int var = window_variant(p, k);
-                  x = __ldg(reinterpret_cast<const float4*>(p.power[var] + window_row(p, var, b, wi, k) * kTok) + q);
-                } else {
-                  x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);  // zero padding: normalises to 0
-                }
-              }
-            } else if (!prenorm) {
-              x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            }
-            r[e] = x;
-          }
-        };
-        auto store_item = [&](int idx, const float4 (&r)[8]) {
-          const int c = idx / kQuads, q = idx % kQuads;
-          float v[4][8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            if (prenorm) {
-              v[0][e] = r[e].x, v[1][e] = r[e].y, v[2][e] = r[e].z, v[3][e] = r[e].w;
+          for (int e = 0; e < 3; ++e) {
+            const int k = T >= 3 ? T - 3 + e : (e < T ? e : -1);
+            if (k >= 0) {
+              const int var = window_variant(p, k);
+              extra[e] = __ldg(p.power[var] + window_row(p, var, b, wi, k) * kTok + tid);
             } else {
-              const bool real = 8 * c + e < kKMel;       // K tail 259..271 must be exact zeros
-              v[0][e] = real ? normalise_db(r[e].x, ref_db, true) : 0.0f;
-              v[1][e] = real ? normalise_db(r[e].y, ref_db, true) : 0.0f;
-              v[2][e] = real ? normalise_db(r[e].z, ref_db, true) : 0.0f;
-              v[3][e] = real ? normalise_db(r[e].w, ref_db, true) : 0.0f;
+              extra[e] = -INFINITY;
             }
           }
+          if (p.n_edge > 0) extra[3] = __ldg(p.power[1] + window_row(p, 1, b, wi, 0) * kTok + tid);
+        }
+        for (int s = 0; s < n_mel_stages; ++s) {
+          mbar_wait(bar_full + 8 * slot, phase);
+          const float* raw = reinterpret_cast<const float*>(smem + kOffRing + slot * kStageBytes);
+          const int rows = min(kMelRows, Tl - kMelRows * s);
+          const int chunks = (rows + 7) >> 3;
+          for (int idx = tid; idx < chunks * kTok; idx += kSimt) {
+            const int c = idx / kTok, j = idx % kTok;
+            float v[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = 4 * q + i;
-            *reinterpret_cast<uint4*>(smem + kOffX + (j >> 3) * kA1Sbo + c * 128 + (j & 7) * 16) = pack8_bf16(v[i]);
+            for (int e = 0; e < 8; ++e)
+              v[e] = 8 * c + e < rows ? normalise_db(raw[(8 * c + e) * kTok + j], ref_db, true) : 0.0f;
+            *reinterpret_cast<uint4*>(smem + kOffX + (j >> 3) * kA1Sbo + (6 * s + c) * 128 + (j & 7) * 16) =
+                pack8_bf16(v);
           }
-        };
-        for (int idx = tid; idx < kItems; idx += 2 * kSimt) {
-          float4 r0[8], r1[8];
-          const bool two = idx + kSimt < kItems;
-          load_item(idx, r0);
-          if (two) load_item(idx + kSimt, r1);
-          store_item(idx, r0);
-          if (two) store_item(idx + kSimt, r1);
+          simt_barrier();                                   // every thread is done reading this ring slot
+          if (tid == 0) mbar_arrive(bar_empty + 8 * slot);
+          if (++slot == kRing) slot = 0, phase ^= 1;
+        }
+        for (int s = 0; s < kStagesPerWindow; ++s)          // the weight stages belong to the MMA thread
+          if (++slot == kRing) slot = 0, phase ^= 1;
+        if (tid < kTok) {
+          const int j = tid;
+          unsigned char* arow = smem + kOffX + (j >> 3) * kA1Sbo + (j & 7) * 16;
+          // K chunks past the long-term frames: zeros up to frame 255, then [short-term x3, 0 x5], then zeros
+          for (int c = (Tl + 7) >> 3; c < 32; ++c) *reinterpret_cast<uint4*>(arow + c * 128) = make_uint4(0, 0, 0, 0);
+          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 3; ++e) v[e] = normalise_db(extra[e], ref_db, true);
+          *reinterpret_cast<uint4*>(arow + 32 * 128) = pack8_bf16(v);
+          *reinterpret_cast<uint4*>(arow + 33 * 128) = make_uint4(0, 0, 0, 0);
+          // edge frames inside the long-term range see zeros beyond the window edge: patch them in place
+          if (p.n_edge > 0) {
+            *reinterpret_cast<__nv_bfloat16*>(arow) = __float2bfloat16_rn(normalise_db(extra[3], ref_db, true));
+            const int k = T - 1;
+            if (k < Tl) {
+              const float x = __ldg(p.power[2] + window_row(p, 2, b, wi, k) * kTok + j);
+              *reinterpret_cast<__nv_bfloat16*>(arow + (k >> 3) * 128 + (k & 7) * 2) =
+                  __float2bfloat16_rn(normalise_db(x, ref_db, true));
+            }
+          }
+        }
+      } else {
+      // ---- A1: Xn[channel j][time t] as bf16.  One item = 8 consecutive frames x 4 consecutive channels:
+        // 8 independent 16-byte loads (frame rows are 320 B apart), then one 16-byte store per channel.
+        // Two items are in flight per thread so that ~32 KB of loads per CTA hide the L2 latency.
+        {
+          constexpr int kQuads = kTok / 4;                 // 20 channel quads per frame
+          constexpr int kItems = kA1Chunks * kQuads;       // 680
+          auto load_item = [&](int idx, float4 (&r)[8]) {
+            const int c = idx / kQuads, q = idx % kQuads;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int t = 8 * c + e;
+              float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (t < kKMel) {
+                if (prenorm) {
+                  if (t >= p.mel_seq)
+                    x = __ldg(reinterpret_cast<const float4*>(p.mel_short + ((size_t)b * 3 + (t - p.mel_seq)) * kTok) + q);
+                  else if (t < p.n_long)
+                    x = __ldg(reinterpret_cast<const float4*>(p.mel_long + ((size_t)b * p.n_frames + t) * kTok) + q);
+                } else {
+                  int k;
+                  if (t < p.mel_seq)
+                    k = t < T ? t : -1;
+                  else {
+                    const int s = t - p.mel_seq;
+                    k = T >= 3 ? T - 3 + s : (s < T ? s : -1);
+                  }
+                  if (k >= 0) {
+                    const int var = window_variant(p, k);
+                    x = __ldg(reinterpret_cast<const float4*>(p.power[var] + window_row(p, var, b, wi, k) * kTok) + q);
+                  } else {
+                    x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);  // zero padding: normalises to 0
+                  }
+                }
+              } else if (!prenorm) {
+                x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+              }
+              r[e] = x;
+            }
+          };
+          auto store_item = [&](int idx, const float4 (&r)[8]) {
+            const int c = idx / kQuads, q = idx % kQuads;
+            float v[4][8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (prenorm) {
+                v[0][e] = r[e].x, v[1][e] = r[e].y, v[2][e] = r[e].z, v[3][e] = r[e].w;
+              } else {
+                const bool real = 8 * c + e < kKMel;       // K tail 259..271 must be exact zeros
+                v[0][e] = real ? normalise_db(r[e].x, ref_db, true) : 0.0f;
+                v[1][e] = real ? normalise_db(r[e].y, ref_db, true) : 0.0f;
+                v[2][e] = real ? normalise_db(r[e].z, ref_db, true) : 0.0f;
+                v[3][e] = real ? normalise_db(r[e].w, ref_db, true) : 0.0f;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = 4 * q + i;
+              *reinterpret_cast<uint4*>(smem + kOffX + (j >> 3) * kA1Sbo + c * 128 + (j & 7) * 16) = pack8_bf16(v[i]);
+            }
+          };
+          for (int idx = tid; idx < kItems; idx += 2 * kSimt) {
+            float4 r0[8], r1[8];
+            const bool two = idx + kSimt < kItems;
+            load_item(idx, r0);
+            if (two) load_item(idx + kSimt, r1);
+            store_item(idx, r0);
+            if (two) store_item(idx + kSimt, r1);
+          }
         }
       }
       fence_async_smem();
       mbar_arrive(bar_go);
+      stamp(ds, 1);
 
       // ---- E1: bias + LayerNorm of token row tid -> enc (bf16, K-major) -------------------------------
       mbar_wait(bar_done, done_phase), done_phase ^= 1;
+      stamp(ds, 2);
       tc_fence_after();
-      if (32 * warp < kTok) {  // warp-uniform: tcgen05.ld is warp-collective; warp 3 owns only padding rows
-        float sum = 0.0f;
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          float v[32];
-          tmem_ld32(lane_taddr + kColD1 + c0, v);
+      {
+        // warp-uniform guard: tcgen05.ld is warp-collective; the wq == 3 warps own only padding rows (96..127)
+        const bool live = 32 * wq < kTok;
+        const int cb = 128 * wg;                       // this warpgroup's half of the 256 features
+        if (live) {
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            float v[32];
+            tmem_ld32(lane_taddr + kColD1 + cb + c0, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sum += v[i] + s_bc[c0 + i];
-        }
-        const float mean = sum * (1.0f / 256);
-        float sq = 0.0f;
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          float v[32];
-          tmem_ld32(lane_taddr + kColD1 + c0, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float d = v[i] + s_bc[c0 + i] - mean;
-            sq = fmaf(d, d, sq);
+            for (int i = 0; i < 32; i += 2) {
+              const float x0 = v[i] + s_bc[cb + c0 + i], x1 = v[i + 1] + s_bc[cb + c0 + i + 1];
+              s0 += x0, s1 += x1;
+              q0 = fmaf(x0, x0, q0), q1 = fmaf(x1, x1, q1);
+            }
           }
+          s_ln[wg * 128 + row] = s0 + s1;
+          s_ln[256 + wg * 128 + row] = q0 + q1;
         }
-        const float rstd = rsqrtf(sq * (1.0f / 256) + W.ln_eps);
-        unsigned char* erow = smem + kOffE + (tid >> 3) * kESbo + (tid & 7) * 16;
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          float v[32];
-          tmem_ld32(lane_taddr + kColD1 + c0, v);
+        simt_barrier();
+        if (live) {
+          const float mean = (s_ln[row] + s_ln[128 + row]) * (1.0f / 256);
+          const float var = fmaxf((s_ln[256 + row] + s_ln[384 + row]) * (1.0f / 256) - mean * mean, 0.0f);
+          const float rstd = rsqrtf(var + W.ln_eps);
+          unsigned char* erow = smem + kOffE + (row >> 3) * kESbo + (row & 7) * 16;
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            float v[32];
+            tmem_ld32(lane_taddr + kColD1 + cb + c0, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = (v[i] + s_bc[c0 + i] - mean) * rstd * s_g[c0 + i] + s_b[c0 + i];
-          if (tid < kTok) {
+            for (int i = 0; i < 32; ++i)
+              v[i] = (v[i] + s_bc[cb + c0 + i] - mean) * rstd * s_g[cb + c0 + i] + s_b[cb + c0 + i];
+            if (row < kTok) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(erow + (c0 / 8 + q) * 128) = pack8_bf16(v + 8 * q);
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(erow + ((cb + c0) / 8 + q) * 128) = pack8_bf16(v + 8 * q);
+            }
           }
         }
       }
       tc_fence_before();
       fence_async_smem();
       mbar_arrive(bar_go);
+      stamp(ds, 3);
 
       // ---- E2 softmax rows -> P tiles;  E3 vT rows (+ bv) -> vT tiles ---------------------------------
       mbar_wait(bar_done, done_phase), done_phase ^= 1;
+      stamp(ds, 4);
       tc_fence_after();
-      for (int t = 0; t < 2; ++t) {
-        // row tid of tile t is (head 4 t + warp, query lane); queries 28..31 are padding
+      {
+        const int t = wg;
+        // row `row` of tile t is (head 4 t + wq, query lane); queries 28..31 are padding
         float s[kTok];
         {
           float v[32];
@@ -449,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         const float inv = lane < KOE_N_MOUTH ? 1.0f / sum : 0.0f;
 #pragma unroll
         for (int i = 0; i < kTok; ++i) s[i] *= inv;
-        unsigned char* prow = smem + kOffX + t * kPTile + (tid >> 3) * kPSbo + (tid & 7) * 16;
+        unsigned char* prow = smem + kOffX + t * kPTile + (row >> 3) * kPSbo + (row & 7) * 16;
 #pragma unroll
         for (int c = 0; c < 10; ++c) *reinterpret_cast<uint4*>(prow + c * 128) = pack8_bf16(s + 8 * c);
         if (p.attn_out != nullptr && lane < KOE_N_MOUTH) {
@@ -458,7 +576,8 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           for (int i = 0; i < kTok; ++i) atomicAdd(dst + i, s[i] * (1.0f / KOE_N_HEADS));
         }
       }
-      for (int t = 0; t < 2; ++t) {
+      {
+        const int t = wg;
         float s[kTok];
         {
           float v[32];
@@ -473,25 +592,28 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
 #pragma unroll
           for (int i = 0; i < 16; ++i) s[64 + i] = u[i];
         }
-        const float bias = s_bv[128 * t + tid];
+        const float bias = s_bv[128 * t + row];
 #pragma unroll
         for (int i = 0; i < kTok; ++i) s[i] += bias;
-        unsigned char* vrow = smem + kOffVT + t * kPTile + (tid >> 3) * kPSbo + (tid & 7) * 16;
+        unsigned char* vrow = smem + kOffVT + t * kPTile + (row >> 3) * kPSbo + (row & 7) * 16;
 #pragma unroll
         for (int c = 0; c < 10; ++c) *reinterpret_cast<uint4*>(vrow + c * 128) = pack8_bf16(s + 8 * c);
       }
       tc_fence_before();
       fence_async_smem();
       mbar_arrive(bar_go);
+      stamp(ds, 5);
 
       // ---- E4: O[h][q][0..31] (diagonal block of tile t) -> Oflat row q, K = 32 h + d -------------------
       mbar_wait(bar_done, done_phase), done_phase ^= 1;
+      stamp(ds, 6);
       tc_fence_after();
-      for (int t = 0; t < 2; ++t) {
+      {
+        const int t = wg;
         float v[32];
-        tmem_ld32(lane_taddr + kColO + 128 * t + 32 * warp, v);
+        tmem_ld32(lane_taddr + kColO + 128 * t + 32 * wq, v);
         if (lane < KOE_N_MOUTH) {
-          const int h = 4 * t + warp;
+          const int h = 4 * t + wq;
           unsigned char* orow = smem + kOffE + (lane >> 3) * kESbo + (lane & 7) * 16 + (4 * h) * 128;
 #pragma unroll
           for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(orow + q * 128) = pack8_bf16(v + 8 * q);
@@ -500,9 +622,11 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       tc_fence_before();
       fence_async_smem();
       mbar_arrive(bar_go);
+      stamp(ds, 7);
 
       // ---- E5: decoder tail on rows 0..27 + fusion -----------------------------------------------------
       mbar_wait(bar_done, done_phase), done_phase ^= 1;
+      stamp(ds, 8);
       tc_fence_after();
       if (warp == 0) {
         float logit = 0.0f;
@@ -526,13 +650,14 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         p.out[o_off] = fminf(fmaxf(__ldg(W.coef + idx) * y, 0.0f), 1.0f);
         if (p.sigmoid_out != nullptr) p.sigmoid_out[o_off] = y;
       }
+      stamp(ds, 9);
       tc_fence_before();
       simt_barrier();  // the next window's A1 staging overwrites the P tiles only after every row is consumed
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
   }
