@@ -56,6 +56,9 @@ typedef struct koe_frontend koe_frontend_t; /* opaque: Hann window, FFT twiddles
 int koe_frontend_create(int device, int sample_rate, int n_fft, int n_mels, float fmin, float fmax,
                         koe_frontend_t** out);
 int koe_frontend_destroy(koe_frontend_t* fe);
+/* 1 when this frontend's filterbank has the structure of the path's default bank (sr 16000, 80 mels, 80..8000 Hz,
+ * simplified_dual_stream_model.py:188-199) and runs the unrolled filterbank phase; 0: generic looped kernel */
+int koe_frontend_uses_unrolled_bank(const koe_frontend_t* fe);
 /* copy the dense (n_mels x (1+n_fft/2)) float32 filterbank to host memory (for parity tests) */
 int koe_frontend_filterbank_host(const koe_frontend_t* fe, float* fb_host);
 

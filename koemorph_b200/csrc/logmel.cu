@@ -6,14 +6,21 @@
 //
 // Kernel design (see DESIGN.md section "K1"):
 //   * one warp transforms TWO real frames of the same clip at once as one complex 1024-point FFT
-//     (z = a + i b), decomposed 32 x 32: radix-32 FFT in registers, twiddle, 32x32 transpose through a
-//     padded shared-memory tile, radix-32 FFT in registers.  After the second pass lane l holds
-//     X[l + 32 r]; the conjugate-symmetric partner X[1024 - k] lives in lane (32 - l) & 31, so the two
-//     real spectra are separated with 32 warp shuffles and no further shared-memory round trip.
-//   * a CTA (8 warps) therefore produces 16 power spectra per iteration, parked in shared memory with
-//     bank-skewed strides; the Slaney filterbank (<= 2 filters per bin, 992 non-zeros) is then applied
-//     by all 8 warps with lanes = 16 frames x 2 adjacent filters (weights broadcast, spectra conflict-free).
-//   * results leave through a shared staging tile as coalesced float4 rows of 80 mel powers.
+//     (z = a + i b), decomposed 32 x 32: radix-2 DIT FFT of 32 points in registers, twiddle, 32x32 transpose
+//     through a padded shared-memory tile, second 32-point FFT in registers.  Every complex value is one
+//     64-bit register pair and every butterfly is written with the packed fp32x2 instructions of sm_100
+//     (FADD2 / FMUL2 / FFMA2, whose operands take per-half negation and a half swap, so "times -i" is free
+//     and a butterfly with a general twiddle is 3 instructions: x = a + w b as two FFMA2, y = 2a - x as one).
+//   * after the second pass lane l holds Z[l + 32 r]; the conjugate-symmetric partner Z[1024 - k] lives in lane
+//     (32 - l) & 31, so the two real spectra are separated with 32 warp shuffles and no further shared-memory
+//     round trip; the pair (|A_k|^2, |B_k|^2) comes out of one FMUL2 + one FFMA2.
+//   * a CTA is 16 warps (register-limited: one CTA per SM) -> 32 power spectra per iteration, parked in the warps'
+//     transposition tiles with bank-skewed bases.  The Slaney filterbank is then applied with lane = frame: the 16
+//     warps split the filter groups, every weight / bin index is a broadcast, every spectrum read is conflict-free
+//     and the control flow is warp-uniform.
+//   * results leave through a shared staging tile as coalesced rows of 80 mel values in dB.
+//   * the audio of the NEXT iteration is loaded into registers before the filterbank phase, so DRAM latency
+//     hides behind it.
 #include <algorithm>
 #include <cmath>
 #include <mutex>
@@ -25,23 +32,25 @@ namespace koe {
 
 constexpr int kFrameLen = 1024;
 constexpr int kBins = 513;
-constexpr int kWarps = 8;
+constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr int kSlots = 2 * kWarps;      // frames per CTA iteration
-constexpr int kXbufStride = 1058;       // floats per warp buffer: >= 32*33, == 2 (mod 32)
-constexpr int kSecondFrame = 513;       // offset of the warp's second spectrum, == 1 (mod 32)
+constexpr int kSlots = 2 * kWarps;      // frames per CTA iteration (= 32: one per lane in the filterbank phase)
+constexpr int kRowF2 = 33;              // float2 per row of the transposition tile (padded: conflict-free both ways)
+constexpr int kScratch = 2120;          // floats per warp tile: >= 2 * 32 * 33, == 8 (mod 32)
+constexpr int kSecondFrame = 516;       // offset of the warp's second spectrum, == 4 (mod 32): with lane = frame the
+                                        // bases of 8 consecutive frames are 16 bytes apart mod 128 -> LDS.128 conflict-free
 constexpr int kMaxBins = 512;           // spectrum bins that carry filterbank weight (507 for 80..8000 Hz)
-constexpr int kRuns = 2 * kWarps;       // the weighted bins are cut into 16 equal runs, two per warp
-constexpr int kTileStride = 81;         // mel accumulator row stride (floats), odd: conflict-free across slots
+constexpr int kMaxGroups = 96;          // groups of consecutive bins feeding the same pair of adjacent filters
+constexpr int kTileStride = 81;         // mel staging row stride (floats), odd: conflict-free across frames
 
 struct FrontendTables {
   const float* hann;     // [1024]
   const float2* tw;      // [32][32] W_1024^(k1*n2)
   // Slaney filterbank, bin-major: a spectrum bin feeds at most two ADJACENT filters (fl, fl + 1)
-  const float2* binw;    // [n_bins] (weight into filter fl, weight into filter fl + 1)
-  const int* binkf;      // [n_bins] bin index k | fl << 16
-  const int* runs;       // [kRuns + 1] run boundaries into the bin list
-  int n_bins;
+  const float2* binw;    // [n_bins] 0.25 * (weight into filter fl, weight into filter fl + 1)
+  const int4* groups;    // [n_groups] {first bin k, first entry of binw, number of bins, fl}: fl rises by one per group
+  const int* runs;       // [kWarps + 1] group range of every warp in the filterbank phase
+  int n_bins, n_groups;
 };
 
 struct LogmelParams {
@@ -61,7 +70,7 @@ __host__ __device__ constexpr int bitrev5(int i) {
   return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
 }
 
-// cos / sin of 2*pi*t/32 for t = 0..15 as literals so the unrolled butterflies use immediates
+// cos(2*pi*t/32) for t = 0..15 as literals so the unrolled butterflies use immediates
 __device__ __forceinline__ float cos32(int t) {
   switch (t) {
     case 0: return 1.0f;
@@ -82,257 +91,344 @@ __device__ __forceinline__ float cos32(int t) {
     default: return -0.98078528040323043f;
   }
 }
-// multiply (tr + i ti) by W_32^t = cos(2 pi t / 32) - i sin(2 pi t / 32); t is a compile-time value after unrolling
-__device__ __forceinline__ void mul_w32(int t, float tr, float ti, float& orr, float& oi) {
+
+// ---- complex arithmetic on (re, im) register pairs with the packed fp32x2 pipe ----------------------------------
+__device__ __forceinline__ float2 bcast(float s) { return make_float2(s, s); }
+// a + w*b and a - w*b for a compile-time twiddle w = W_32^t = cos(2 pi t/32) - i sin(2 pi t/32)
+__device__ __forceinline__ void butterfly(int t, float2& a, float2& b) {
   if (t == 0) {
-    orr = tr;
-    oi = ti;
-  } else if (t == 8) {  // -i
-    orr = ti;
-    oi = -tr;
-  } else if (t == 4) {  // (1 - i)/sqrt2
-    const float c = 0.70710678118654752f;
-    orr = c * (tr + ti);
-    oi = c * (ti - tr);
-  } else if (t == 12) {  // (-1 - i)/sqrt2
-    const float c = 0.70710678118654752f;
-    orr = c * (ti - tr);
-    oi = -c * (tr + ti);
+    const float2 x = __fadd2_rn(a, b);
+    b = __fadd2_rn(a, make_float2(-b.x, -b.y));
+    a = x;
+  } else if (t == 8) {  // w = -i: w*b = (b.y, -b.x)
+    const float2 x = __fadd2_rn(a, make_float2(b.y, -b.x));
+    b = __fadd2_rn(a, make_float2(-b.y, b.x));
+    a = x;
   } else {
     const float wr = cos32(t);
-    const float ws = cos32(t > 8 ? t - 8 : 8 - t);  // sin(2 pi t/32) = cos(2 pi (t-8)/32), cos even
-    orr = tr * wr + ti * ws;
-    oi = ti * wr - tr * ws;
+    const float ws = cos32(t > 8 ? t - 8 : 8 - t);  // sin(2 pi t/32)
+    // w*b = (wr b.x + ws b.y, wr b.y - ws b.x)
+    float2 x = __ffma2_rn(b, bcast(wr), a);
+    x = __ffma2_rn(make_float2(b.y, -b.x), bcast(ws), x);
+    b = __ffma2_rn(a, bcast(2.0f), make_float2(-x.x, -x.y));
+    a = x;
   }
 }
 
-// In-register radix-2 decimation-in-frequency FFT of 32 complex values (forward, e^{-i...}).
-// On return element i holds X[bitrev5(i)].
-__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
+// In-register radix-2 decimation-in-time FFT of 32 complex values (forward, e^{-i...}).
+// On entry element i holds x[bitrev5(i)]; on return element k holds X[k].
+__device__ __forceinline__ void fft32(float2 (&v)[32]) {
 #pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
+  for (int h = 1; h <= 16; h <<= 1) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      if ((i & s) == 0) {
-        const int j = i + s;
-        const int t = (i & (s - 1)) * (16 / s);
-        const float ar = re[i], ai = im[i], br = re[j], bi = im[j];
-        re[i] = ar + br;
-        im[i] = ai + bi;
-        mul_w32(t, ar - br, ai - bi, re[j], im[j]);
-      }
+      if ((i & h) == 0) butterfly((i & (h - 1)) * (16 / h), v[i], v[i + h]);
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+// Where a frame pair lives: clip, first frame (< 0: no pair), first sample of both frames, valid sample ranges.
+struct PairInfo {
+  int clip, frame;
+  int fa_lo, fb_lo;            // first sample of frame A / frame B (may be negative)
+  int lo_a, hi_a, lo_b, hi_b;  // samples outside [lo, hi) read as zero (or are reflected, pad_mode 1)
+  bool interior, has_b;
+};
+
+__device__ __forceinline__ PairInfo locate_pair(const LogmelParams& p, unsigned pair, unsigned total_pairs, unsigned ppc) {
+  PairInfo pi;
+  pi.clip = 0;
+  pi.frame = -1;
+  pi.interior = false;
+  if (pair >= total_pairs) return pi;
+  const int b = (int)(pair / ppc);
+  const int ga = 2 * (int)(pair - (unsigned)b * ppc);
+  pi.clip = b;
+  pi.frame = ga;
+  pi.has_b = ga + 1 < p.n_frames;
+  const int fa = p.frame_offset + ga * p.frame_step, fb = fa + p.frame_step;  // frame indices in hops
+  pi.lo_a = 0, pi.hi_a = p.n_samples, pi.lo_b = 0, pi.hi_b = p.n_samples;
+  if (p.lo_rel != KOE_NO_EDGE) {
+    pi.lo_a = max(pi.lo_a, p.sample_offset + (fa + p.lo_rel) * p.hop);
+    pi.lo_b = max(pi.lo_b, p.sample_offset + (fb + p.lo_rel) * p.hop);
+  }
+  if (p.hi_rel != KOE_NO_EDGE) {
+    pi.hi_a = min(pi.hi_a, p.sample_offset + (fa + p.hi_rel) * p.hop);
+    pi.hi_b = min(pi.hi_b, p.sample_offset + (fb + p.hi_rel) * p.hop);
+  }
+  if (!pi.has_b) pi.hi_b = pi.lo_b;  // empty range: second frame reads as silence
+  pi.fa_lo = p.sample_offset + fa * p.hop - kFrameLen / 2;
+  pi.fb_lo = p.sample_offset + fb * p.hop - kFrameLen / 2;
+  pi.interior = pi.fa_lo >= pi.lo_a && pi.fa_lo + kFrameLen <= pi.hi_a && pi.fb_lo >= pi.lo_b &&
+                pi.fb_lo + kFrameLen <= pi.hi_b;
+  return pi;
+}
+
+// interior frames (all but the first / last of a clip): no masking.  v[bitrev5(n1)] = (a[32 n1 + lane], b[32 n1 + lane])
+__device__ __forceinline__ void load_interior(const LogmelParams& p, const PairInfo& pi, int lane, float2 (&v)[32]) {
+  const float* clip = p.audio + (long long)pi.clip * p.audio_stride;
+  const float* __restrict__ pa = clip + pi.fa_lo + lane;
+  const float* __restrict__ pb = clip + pi.fb_lo + lane;
+#pragma unroll
+  for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = make_float2(__ldg(pa + 32 * n1), __ldg(pb + 32 * n1));
+}
+
+// frames that touch a clip / window edge (~2 pairs per clip): masked or reflected samples, staged through the warp's
+// shared-memory tile as tile[n1 * 32 + lane] = (a, b); out of line and not unrolled to keep the hot loop small
+__device__ __noinline__ void load_edge(const float* __restrict__ clip, int n_samples, int pad_mode, int fa_lo, int fb_lo,
+                                       int lo_a, int hi_a, int lo_b, int hi_b, float2* tile) {
+  const int lane = threadIdx.x & 31;
+  const int last = n_samples - 1;
+#pragma unroll 1
+  for (int n1 = 0; n1 < 32; ++n1) {
+    int sa = fa_lo + lane + 32 * n1, sb = fb_lo + lane + 32 * n1;
+    bool oka, okb;
+    if (pad_mode == 1) {  // numpy "reflect" padding about the first / last sample (MelSlidingWindowExtractor default)
+      sa = sa < 0 ? -sa : (sa > last ? 2 * last - sa : sa);
+      sb = sb < 0 ? -sb : (sb > last ? 2 * last - sb : sb);
+      oka = sa >= 0 && sa <= last;
+      okb = hi_b > lo_b && sb >= 0 && sb <= last;
+    } else {
+      oka = sa >= lo_a && sa < hi_a;
+      okb = sb >= lo_b && sb < hi_b;
+    }
+    tile[n1 * 32 + lane] = make_float2(oka ? __ldg(clip + sa) : 0.0f, okb ? __ldg(clip + sb) : 0.0f);
+  }
+}
+
+__device__ __forceinline__ float db_from_power(float p) {
+  // 10 log10(max(p, amin)) = (10 log10 2) * log2(.): the argument is a normal number, MUFU.LG2 is within 2 ulp
+  return 3.0102999566398120f * __log2f(fmaxf(p, kAmin));
+}
+// order-preserving map float -> int32, so that a warp maximum is one REDUX
+__device__ __forceinline__ int float_order(float f) {
+  const int i = __float_as_int(f);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float order_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+// ---- filterbank phase, default bank: straight-line code from the compile-time structure ---------------------------
+#include "melbank_default.inc"
+// 0.25 * float32 weights of the default bank: entry i belongs to bin kDefFirstBin + i, (.x, .y) feed filters (g, g + 1).
+// Written by koe_frontend_create; read as constant-bank operands of the FFMAs (the index is a literal after unrolling).
+__constant__ float2 c_binw[kMaxBins];
+
+template <int W>
+__device__ __forceinline__ void mel_run_default(const float* __restrict__ spec, float* __restrict__ tlo,
+                                                float* __restrict__ thi) {
+  constexpr int b0 = kDefRunBinDev[W], b1 = kDefRunBinDev[W + 1];
+  if (b0 >= b1) return;
+  float lo = 0.0f, hi = 0.0f;
+#pragma unroll
+  for (int k4 = (b0 & ~3); k4 < b1; k4 += 4) {
+    const float4 x4 = *reinterpret_cast<const float4*>(spec + k4);
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k4 + j;
+      if (k >= b0 && k < b1) {
+        if (k > b0 && kDefBinGroupDev[k] != kDefBinGroupDev[k - 1]) {  // next interval: retire the falling / rising halves
+          tlo[kDefBinGroupDev[k - 1]] = lo;
+          thi[kDefBinGroupDev[k - 1] + 1] = hi;
+          lo = 0.0f;
+          hi = 0.0f;
+        }
+        const float2 w = c_binw[k - kDefFirstBin];
+        lo = fmaf(w.x, xs[j], lo);
+        hi = fmaf(w.y, xs[j], hi);
+      }
+    }
+  }
+  tlo[kDefBinGroupDev[b1 - 1]] = lo;
+  thi[kDefBinGroupDev[b1 - 1] + 1] = hi;  // the rising half of "filter 80" lands in the spare column of the tile
+}
+
+__device__ __forceinline__ void mel_phase_default(int warp, const float* spec, float* tlo, float* thi) {
+  switch (warp) {
+    case 0: mel_run_default<0>(spec, tlo, thi); break;
+    case 1: mel_run_default<1>(spec, tlo, thi); break;
+    case 2: mel_run_default<2>(spec, tlo, thi); break;
+    case 3: mel_run_default<3>(spec, tlo, thi); break;
+    case 4: mel_run_default<4>(spec, tlo, thi); break;
+    case 5: mel_run_default<5>(spec, tlo, thi); break;
+    case 6: mel_run_default<6>(spec, tlo, thi); break;
+    case 7: mel_run_default<7>(spec, tlo, thi); break;
+    case 8: mel_run_default<8>(spec, tlo, thi); break;
+    case 9: mel_run_default<9>(spec, tlo, thi); break;
+    case 10: mel_run_default<10>(spec, tlo, thi); break;
+    case 11: mel_run_default<11>(spec, tlo, thi); break;
+    case 12: mel_run_default<12>(spec, tlo, thi); break;
+    case 13: mel_run_default<13>(spec, tlo, thi); break;
+    case 14: mel_run_default<14>(spec, tlo, thi); break;
+    default: mel_run_default<15>(spec, tlo, thi); break;
+  }
+}
+
+// generic bank (any other sample rate / band edges): warp-uniform loops over the group table
+__device__ __forceinline__ void mel_phase_generic(int g, int gend, const int4* s_groups, const float2* s_binw,
+                                                  const float* spec, float* tlo, float* thi) {
+  for (; g < gend; ++g) {
+    const int4 gi = s_groups[g];
+    const float* x = spec + gi.x;
+    const float2* w = s_binw + gi.y;
+    float lo = 0.0f, hi = 0.0f;
+    for (int i = 0; i < gi.z; ++i) {
+      const float xv = x[i];
+      const float2 wv = w[i];
+      lo = fmaf(wv.x, xv, lo);
+      hi = fmaf(wv.y, xv, hi);
+    }
+    tlo[gi.w] = lo;
+    thi[gi.w + 1] = hi;
+  }
+}
+
+template <bool kDefaultBank>
+__global__ void __launch_bounds__(kThreads, 1)
 logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_hann = reinterpret_cast<float*>(smem_raw);              // 1024
   float2* s_tw = reinterpret_cast<float2*>(s_hann + kFrameLen);    // 1024 float2
   float2* s_binw = s_tw + 1024;                                    // kMaxBins float2
-  int* s_binkf = reinterpret_cast<int*>(s_binw + kMaxBins);        // kMaxBins
-  int* s_runs = s_binkf + kMaxBins;                                // kRuns + 1 (+ pad to 24)
-  float* s_xbuf = reinterpret_cast<float*>(s_runs + 24);           // kWarps * kXbufStride
-  float* s_tile = s_xbuf + kWarps * kXbufStride;                   // kSlots * kTileStride mel accumulators
+  int4* s_groups = reinterpret_cast<int4*>(s_binw + kMaxBins);     // kMaxGroups
+  int* s_runs = reinterpret_cast<int*>(s_groups + kMaxGroups);     // kWarps + 1 (+ pad to 32)
+  float* s_tlo = reinterpret_cast<float*>(s_runs + 32);            // kSlots * kTileStride: falling halves (filter g of group g)
+  float* s_thi = s_tlo + kSlots * kTileStride;                     // kSlots * kTileStride: rising halves (filter g + 1)
+  float* s_scratch = s_thi + kSlots * kTileStride;                 // kWarps * kScratch, 16-byte aligned, bank 0
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int i = tid; i < kFrameLen; i += kThreads) s_hann[i] = tab.hann[i];
   for (int i = tid; i < 1024; i += kThreads) s_tw[i] = tab.tw[i];
-  for (int i = tid; i < tab.n_bins; i += kThreads) {
-    s_binw[i] = tab.binw[i];
-    s_binkf[i] = tab.binkf[i];
-  }
-  if (tid <= kRuns) s_runs[tid] = tab.runs[tid];
+  for (int i = tid; i < tab.n_bins; i += kThreads) s_binw[i] = tab.binw[i];
+  for (int i = tid; i < tab.n_groups; i += kThreads) s_groups[i] = tab.groups[i];
+  if (tid <= kWarps) s_runs[tid] = tab.runs[tid];
+  if (tid < kSlots) s_thi[tid * kTileStride] = 0.0f;  // filter 0 has no rising half from a lower interval
   __syncthreads();
 
-  const int ppc = (p.n_frames + 1) >> 1;  // frame pairs per clip
-  const long long total_pairs = (long long)p.n_clips * ppc;
-  const long long n_blocks = (total_pairs + kWarps - 1) / kWarps;
-  float* xb = s_xbuf + warp * kXbufStride;
+  const unsigned ppc = (unsigned)(p.n_frames + 1) >> 1;  // frame pairs per clip
+  const unsigned total_pairs = (unsigned)p.n_clips * ppc;
+  const unsigned n_iters = (total_pairs + kWarps - 1) / kWarps;
+  float* xb = s_scratch + warp * kScratch;
+  float2* xb2 = reinterpret_cast<float2*>(xb);
 
-  for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-    for (int i = tid; i < kSlots * kTileStride; i += kThreads) s_tile[i] = 0.0f;  // consumed after two barriers
+  float2 v[32];
+  unsigned it = blockIdx.x;
+  PairInfo nxt = locate_pair(p, it < n_iters ? it * kWarps + warp : total_pairs, total_pairs, ppc);
+  if (nxt.interior) load_interior(p, nxt, lane, v);
+
+  for (; it < n_iters; it += gridDim.x) {
     // ------------------------------------------------------------------ FFT phase (per warp)
-    const long long pair = blk * kWarps + warp;
-    if (pair < total_pairs) {
-      const int b = (int)(pair / ppc);
-      const int ga = 2 * (int)(pair % ppc);
-      const bool has_b = ga + 1 < p.n_frames;
-      const float* clip = p.audio + (long long)b * p.audio_stride;
-      const int fa = p.frame_offset + ga * p.frame_step, fb = fa + p.frame_step;  // frame indices in hops
-      int lo_a = 0, hi_a = p.n_samples, lo_b = 0, hi_b = p.n_samples;
-      if (p.lo_rel != KOE_NO_EDGE) {
-        lo_a = max(lo_a, p.sample_offset + (fa + p.lo_rel) * p.hop);
-        lo_b = max(lo_b, p.sample_offset + (fb + p.lo_rel) * p.hop);
+    const PairInfo cur = nxt;
+    if (cur.frame >= 0) {
+      if (!cur.interior) {
+        load_edge(p.audio + (long long)cur.clip * p.audio_stride, p.n_samples, p.pad_mode, cur.fa_lo, cur.fb_lo, cur.lo_a,
+                  cur.hi_a, cur.lo_b, cur.hi_b, xb2);
+        __syncwarp();
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = xb2[n1 * 32 + lane];
+        __syncwarp();
       }
-      if (p.hi_rel != KOE_NO_EDGE) {
-        hi_a = min(hi_a, p.sample_offset + (fa + p.hi_rel) * p.hop);
-        hi_b = min(hi_b, p.sample_offset + (fb + p.hi_rel) * p.hop);
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = __fmul2_rn(v[bitrev5(n1)], bcast(s_hann[32 * n1 + lane]));
+      fft32(v);  // v[k1] = Y[k1] of column n2 = lane
+#pragma unroll
+      for (int k1 = 1; k1 < 32; ++k1) {
+        const float2 w = s_tw[k1 * 32 + lane];  // W_1024^(k1 * n2)
+        const float2 z = v[k1];
+        float2 r = __fmul2_rn(z, bcast(w.x));
+        v[k1] = __ffma2_rn(make_float2(-z.y, z.x), bcast(w.y), r);
       }
-      if (!has_b) hi_b = lo_b;  // empty range: second frame reads as silence
-      const int fa_lo = p.sample_offset + fa * p.hop - kFrameLen / 2;  // first sample of each frame
-      const int fb_lo = p.sample_offset + fb * p.hop - kFrameLen / 2;
-      const int sa0 = fa_lo + lane, sb0 = fb_lo + lane;
-
-      float re[32], im[32];
-      if (fa_lo >= lo_a && fa_lo + kFrameLen <= hi_a && fb_lo >= lo_b && fb_lo + kFrameLen <= hi_b) {
-        // interior frames (all but the first / last of a clip): no masking, one base pointer per frame
-        const float* __restrict__ pa = clip + sa0;
-        const float* __restrict__ pb = clip + sb0;
+      // 32x32 transpose of complex values through the warp's padded tile
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          const float w = s_hann[32 * n1 + lane];
-          re[n1] = __ldg(pa + 32 * n1) * w;
-          im[n1] = __ldg(pb + 32 * n1) * w;
-        }
-      } else if (p.pad_mode == 1) {
-        // numpy "reflect" padding about the first / last sample (MelSlidingWindowExtractor default)
-        const int last = p.n_samples - 1;
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          int sa = sa0 + 32 * n1, sb = sb0 + 32 * n1;
-          sa = sa < 0 ? -sa : (sa > last ? 2 * last - sa : sa);
-          sb = sb < 0 ? -sb : (sb > last ? 2 * last - sb : sb);
-          const float w = s_hann[32 * n1 + lane];
-          const float va = (sa >= 0 && sa <= last) ? __ldg(clip + sa) : 0.0f;
-          const float vb = (has_b && sb >= 0 && sb <= last) ? __ldg(clip + sb) : 0.0f;
-          re[n1] = va * w;
-          im[n1] = vb * w;
-        }
-      } else {
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          const int sa = sa0 + 32 * n1, sb = sb0 + 32 * n1;
-          const float w = s_hann[32 * n1 + lane];
-          const float va = (sa >= lo_a && sa < hi_a) ? __ldg(clip + sa) : 0.0f;
-          const float vb = (sb >= lo_b && sb < hi_b) ? __ldg(clip + sb) : 0.0f;
-          re[n1] = va * w;
-          im[n1] = vb * w;
-        }
-      }
-      fft32(re, im);  // element i = Y[k1 = bitrev5(i)] for column n2 = lane
-#pragma unroll
-      for (int i = 1; i < 32; ++i) {
-        const float2 w = s_tw[bitrev5(i) * 32 + lane];  // W_1024^(k1 * n2)
-        const float tr = re[i], ti = im[i];
-        re[i] = tr * w.x - ti * w.y;
-        im[i] = tr * w.y + ti * w.x;
-      }
-      // 32x32 transpose, real plane then imaginary plane, through the warp's padded tile
+      for (int k1 = 0; k1 < 32; ++k1) xb2[k1 * kRowF2 + lane] = v[k1];
       __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) xb[bitrev5(i) * 33 + lane] = re[i];
+      for (int n2 = 0; n2 < 32; ++n2) v[bitrev5(n2)] = xb2[lane * kRowF2 + n2];
       __syncwarp();
-#pragma unroll
-      for (int n2 = 0; n2 < 32; ++n2) re[n2] = xb[lane * 33 + n2];
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) xb[bitrev5(i) * 33 + lane] = im[i];
-      __syncwarp();
-#pragma unroll
-      for (int n2 = 0; n2 < 32; ++n2) im[n2] = xb[lane * 33 + n2];
-      __syncwarp();
-      fft32(re, im);  // element i = Z[lane + 32 * bitrev5(i)]
+      fft32(v);  // v[k2] = Z[lane + 32 * k2]
 
       // separate the two real spectra: partner of k = lane + 32 r is 1024 - k = ((32-lane)&31) + 32 r'
       const int src = (32 - lane) & 31;
-      float pr[16], pi[16];
+      float2 q[16];
 #pragma unroll
       for (int s = 0; s < 16; ++s) {
-        pr[s] = __shfl_sync(kFullMask, re[bitrev5(16 + s)], src);
-        pi[s] = __shfl_sync(kFullMask, im[bitrev5(16 + s)], src);
+        q[s].x = __shfl_sync(kFullMask, v[16 + s].x, src);
+        q[s].y = __shfl_sync(kFullMask, v[16 + s].y, src);
       }
       float* pa = xb;
       float* pb = xb + kSecondFrame;
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        const float zr = re[bitrev5(r)], zi = im[bitrev5(r)];
+        const float2 z = v[r];
         // lanes 1..31: partner register r' = 31 - r (slot 15 - r); lane 0: r' = 32 - r (slot 16 - r), r = 0 is its own partner
-        float qr = pr[15 - r], qi = pi[15 - r];
-        if (lane == 0) {
-          qr = (r == 0) ? zr : pr[(16 - r) & 15];
-          qi = (r == 0) ? zi : pi[(16 - r) & 15];
-        }
-        const float ar = zr + qr, ai = zi - qi, br = zi + qi, bi = zr - qr;
-        pa[lane + 32 * r] = 0.25f * (ar * ar + ai * ai);
-        pb[lane + 32 * r] = 0.25f * (br * br + bi * bi);
+        float2 c = q[15 - r];
+        if (lane == 0) c = (r == 0) ? z : q[(16 - r) & 15];
+        // 2A = z + conj(c), 2iB = z - conj(c): (4|A|^2, 4|B|^2) = u*u + w*w, u = (z.x + c.x, z.x - c.x), w = (z.y - c.y, z.y + c.y)
+        const float2 u = __fadd2_rn(bcast(z.x), make_float2(c.x, -c.x));
+        const float2 w = __fadd2_rn(bcast(z.y), make_float2(-c.y, c.y));
+        const float2 pw = __ffma2_rn(w, w, __fmul2_rn(u, u));
+        pa[lane + 32 * r] = pw.x;
+        pb[lane + 32 * r] = pw.y;
       }
-      if (lane == 0) {  // Nyquist bin 512 = register r = 16, self-paired
-        const float zr = re[bitrev5(16)], zi = im[bitrev5(16)];
-        pa[512] = zr * zr;
-        pb[512] = zi * zi;
+      if (lane == 0) {  // Nyquist bin 512 = register 16, self-paired: A = z.x, B = z.y (x4 like the others)
+        pa[512] = 4.0f * v[16].x * v[16].x;
+        pb[512] = 4.0f * v[16].y * v[16].y;
       }
     }
+    // audio of the next iteration: in flight during the filterbank / store phases
+    nxt = locate_pair(p, it + gridDim.x < n_iters ? (it + gridDim.x) * kWarps + warp : total_pairs, total_pairs, ppc);
+    if (nxt.interior) load_interior(p, nxt, lane, v);
     __syncthreads();
 
-    // ------------------------------------------------------------------ mel phase (whole CTA)
-    // lane = (frame slot, run): walk the run's bins once, feeding the two adjacent filters each bin touches;
-    // runs are cut on interval boundaries, so a filter receives at most two partial sums (its rising half from one
-    // run, its falling half from the same or the next) and the float atomics are order-free: 0 + a + b == 0 + b + a.
+    // ------------------------------------------------------------------ mel phase: lane = frame slot, warp = run of bins
     {
-      const int slot = lane & 15, run = 2 * warp + (lane >> 4);
-      const float* spec = s_xbuf + (slot >> 1) * kXbufStride + (slot & 1) * kSecondFrame;
-      float* trow = s_tile + slot * kTileStride;
-      int i = s_runs[run];
-      const int iend = s_runs[run + 1];
-      int fl = i < iend ? (s_binkf[i] >> 16) : 0;
-      float acc_lo = 0.0f, acc_hi = 0.0f;
-      for (; i < iend; ++i) {
-        const int kf = s_binkf[i];
-        const int f = kf >> 16;
-        if (f != fl) {
-          atomicAdd(trow + fl, acc_lo);
-          if (f == fl + 1) {
-            acc_lo = acc_hi;
-          } else {
-            if (fl + 1 < KOE_N_MELS) atomicAdd(trow + fl + 1, acc_hi);
-            acc_lo = 0.0f;
-          }
-          acc_hi = 0.0f;
-          fl = f;
-        }
-        const float2 w = s_binw[i];
-        const float x = spec[kf & 0xffff];
-        acc_lo = fmaf(w.x, x, acc_lo);
-        acc_hi = fmaf(w.y, x, acc_hi);
-      }
-      atomicAdd(trow + fl, acc_lo);
-      if (fl + 1 < KOE_N_MELS) atomicAdd(trow + fl + 1, acc_hi);
+      const float* spec = s_scratch + (lane >> 1) * kScratch + (lane & 1) * kSecondFrame;
+      if (kDefaultBank)
+        mel_phase_default(warp, spec, s_tlo + lane * kTileStride, s_thi + lane * kTileStride);
+      else
+        mel_phase_generic(s_runs[warp], s_runs[warp + 1], s_groups, s_binw, spec, s_tlo + lane * kTileStride,
+                          s_thi + lane * kTileStride);
     }
     __syncthreads();
 
     // ------------------------------------------------------------------ store phase: warp w owns slots 2w, 2w+1
-    {
-      const long long pr_ = blk * kWarps + warp;
-      if (pr_ < total_pairs) {
-        const int b = (int)(pr_ / ppc);
+    if (cur.frame >= 0) {
+      const float* tlo = s_tlo + (2 * warp) * kTileStride;
+      const float* thi = s_thi + (2 * warp) * kTileStride;
+      float* dst = p.power + (long long)cur.clip * p.power_clip_stride + (long long)cur.frame * KOE_N_MELS;
+      // the 160 values of the two rows (row B follows row A in the clip's block), five per lane: j = lane + 32 q;
+      // j < 80 -> frame A filter j, else frame B filter j - 80, which sits kTileStride - 80 = 1 float further in the tile
+      float mx_a = -INFINITY, mx_b = -INFINITY;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int g = 2 * (int)(pr_ % ppc) + h;
-          if (g < p.n_frames) {
-            const float* trow = s_tile + (2 * warp + h) * kTileStride;
-            float* dst = p.power + (long long)b * p.power_clip_stride + (long long)g * KOE_N_MELS;
-            // stored in dB: 10 log10(max(power, amin)); the consumer only subtracts its reference and clamps
-            const float v0 = power_db(trow[lane]), v1 = power_db(trow[lane + 32]);
-            const float v2 = lane < 16 ? power_db(trow[lane + 64]) : -INFINITY;
-            dst[lane] = v0;
-            dst[lane + 32] = v1;
-            if (lane < 16) dst[lane + 64] = v2;
-            const float mx = warp_max(fmaxf(fmaxf(v0, v1), v2));
-            if (lane == 0 && p.frame_max != nullptr) p.frame_max[(long long)b * p.fmax_clip_stride + g] = mx;
-          }
+      for (int qd = 0; qd < 5; ++qd) {
+        const int j = lane + 32 * qd;
+        const bool second = qd > 2 || (qd == 2 && lane >= KOE_N_MELS - 64);
+        const int t = j + (second ? kTileStride - KOE_N_MELS : 0);
+        // stored in dB: the consumer only subtracts its reference and clamps
+        const float db = db_from_power(tlo[t] + thi[t]);
+        if (!second) {
+          mx_a = fmaxf(mx_a, db);
+          dst[j] = db;
+        } else {
+          mx_b = fmaxf(mx_b, db);
+          if (cur.has_b) dst[j] = db;
         }
       }
+      if (p.frame_max != nullptr) {
+        const int ia = __reduce_max_sync(kFullMask, float_order(mx_a));
+        const int ib = __reduce_max_sync(kFullMask, float_order(mx_b));
+        float* fm = p.frame_max + (long long)cur.clip * p.fmax_clip_stride + cur.frame;
+        if (lane == 0) fm[0] = order_float(ia);
+        if (lane == 1 && cur.has_b) fm[1] = order_float(ib);
+      }
     }
-    __syncthreads();
   }
 }
 
 constexpr size_t kLogmelSmem = sizeof(float) * kFrameLen + sizeof(float2) * 1024 + sizeof(float2) * kMaxBins +
-                               sizeof(int) * (kMaxBins + 24) +
-                               sizeof(float) * (kWarps * kXbufStride + kSlots * kTileStride);
+                               sizeof(int4) * kMaxGroups + sizeof(int) * 32 +
+                               sizeof(float) * (2 * kSlots * kTileStride + kWarps * kScratch);
 
 // ---- dB normalisation: ref = clip max, clamp, rescale; emits long-term and last-3 short-term features
 __global__ void logmel_normalise_kernel(const float* __restrict__ power, const float* __restrict__ frame_max,
@@ -427,8 +523,9 @@ struct koe_frontend {
   float* d_hann = nullptr;
   float2* d_tw = nullptr;
   float2* d_binw = nullptr;
-  int* d_tables = nullptr;  // binkf[kMaxBins] | runs[kRuns + 1]
-  int n_bins = 0;
+  int* d_tables = nullptr;  // groups[kMaxGroups] (int4) | runs[kWarps + 1 -> 32]
+  int n_bins = 0, n_groups = 0;
+  bool default_bank = false;  // structure == melbank_default.inc: the unrolled filterbank phase applies
   int num_sms = 0, occupancy = 0;
   std::vector<float> fb_host;
 };
@@ -458,39 +555,69 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
   fe->fmax = fmax;
   fe->fb_host = slaney_filterbank(sample_rate, n_fft, n_mels, fmin, fmax);
 
-  // bin-major sparse filterbank: every weighted bin feeds one filter or two adjacent ones
+  // bin-major sparse filterbank: every weighted bin feeds one filter or two adjacent ones (fl, fl + 1); consecutive bins
+  // with the same fl form a group (the interval between two filter centres), and fl rises by one from group to group
   std::vector<float2> binw;
-  std::vector<int> tables(kMaxBins + kRuns + 1, 0);
-  for (int k = 0; k < kBins; ++k) {
-    int first = -1, count = 0, last = -1;
-    for (int m = 0; m < n_mels; ++m)
-      if (fe->fb_host[(size_t)m * kBins + k] > 0.0f) {
-        if (first < 0) first = m;
-        last = m;
-        ++count;
+  std::vector<int> tables(4 * kMaxGroups + 32, 0);
+  std::vector<unsigned char> bin_group(kBins, 255);
+  int n_groups = 0;
+  auto unsupported = [&](const char* why, int k) {
+    delete fe;
+    cudaSetDevice(prev);
+    return fail(KOE_E_UNSUPPORTED, "koe_frontend_create: filterbank is not a bank of adjacent triangles (%s at bin %d)", why, k);
+  };
+  {
+    int prev_k = -1, prev_fl = -1;
+    for (int k = 0; k < kBins; ++k) {
+      int first = -1, count = 0, last = -1;
+      for (int m = 0; m < n_mels; ++m)
+        if (fe->fb_host[(size_t)m * kBins + k] > 1e-12f) {  // (a band edge that falls on a bin leaves ~1e-17 there)
+          if (first < 0) first = m;
+          last = m;
+          ++count;
+        }
+      if (count == 0) continue;
+      if (count > 2 || last - first > 1) return unsupported("more than two / non-adjacent filters", k);
+      if ((int)binw.size() >= kMaxBins) return unsupported("too many weighted bins", k);
+      if (prev_k >= 0 && k != prev_k + 1) return unsupported("gap in the weighted bins", k);
+      if (first != prev_fl) {
+        if (first != prev_fl + 1) return unsupported("filters skipped", k);
+        if (n_groups >= kMaxGroups) return unsupported("too many groups", k);
+        tables[4 * n_groups + 0] = k;
+        tables[4 * n_groups + 1] = (int)binw.size();
+        tables[4 * n_groups + 2] = 0;
+        tables[4 * n_groups + 3] = first;
+        ++n_groups;
       }
-    if (count == 0) continue;
-    if (count > 2 || last - first > 1 || (int)binw.size() >= kMaxBins) {
-      delete fe;
-      cudaSetDevice(prev);
-      return fail(KOE_E_UNSUPPORTED, "koe_frontend_create: filterbank is not a bank of adjacent triangles at bin %d", k);
+      ++tables[4 * (n_groups - 1) + 2];
+      bin_group[k] = (unsigned char)first;
+      // 0.25: the kernel leaves 4 |X|^2 in the spectrum (exact power-of-two scaling)
+      binw.push_back(make_float2(0.25f * fe->fb_host[(size_t)first * kBins + k],
+                                 count == 2 ? 0.25f * fe->fb_host[(size_t)last * kBins + k] : 0.0f));
+      prev_k = k;
+      prev_fl = first;
     }
-    tables[binw.size()] = k | (first << 16);
-    binw.push_back(make_float2(fe->fb_host[(size_t)first * kBins + k],
-                               count == 2 ? fe->fb_host[(size_t)last * kBins + k] : 0.0f));
+    if (n_groups != n_mels) return unsupported("a filter without a falling half", kBins);
   }
   fe->n_bins = (int)binw.size();
-  // run boundaries on filter-interval boundaries (where fl changes), as balanced as that allows: then a
-  // filter's rising half lies in one run and its falling half in the same or the next run -> <= 2 partial sums
+  fe->n_groups = n_groups;
+  // runs: contiguous group ranges, one per warp, balanced on bins + a per-group overhead (generic kernel only)
   {
+    int* runs = tables.data() + 4 * kMaxGroups;
+    auto cost = [&](int g) { return 3 + tables[4 * g + 2]; };
+    long long total = 0;
+    for (int g = 0; g < n_groups; ++g) total += cost(g);
+    long long acc = 0;
     int r = 1;
-    tables[kMaxBins] = 0;
-    for (int i = 1; i < fe->n_bins && r < kRuns; ++i) {
-      const bool boundary = (tables[i] >> 16) != (tables[i - 1] >> 16);
-      if (boundary && (long long)i * kRuns >= (long long)fe->n_bins * r) tables[kMaxBins + r++] = i;
+    runs[0] = 0;
+    for (int g = 0; g < n_groups && r < kWarps; ++g) {
+      acc += cost(g);
+      if (acc * kWarps >= total * r) runs[r++] = g + 1;
     }
-    for (; r <= kRuns; ++r) tables[kMaxBins + r] = fe->n_bins;
+    for (; r <= kWarps; ++r) runs[r] = n_groups;
   }
+  fe->default_bank = fe->n_bins == kDefNumBins && tables[0] == kDefFirstBin &&
+                     std::equal(bin_group.begin(), bin_group.end(), kDefBinGroup);
   std::vector<float> hann(kFrameLen);
   for (int n = 0; n < kFrameLen; ++n) hann[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / kFrameLen));
   std::vector<float2> tw(1024);
@@ -510,13 +637,17 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
   binw.resize(kMaxBins, make_float2(0.f, 0.f));
   up((void**)&fe->d_binw, binw.data(), binw.size() * sizeof(float2));
   up((void**)&fe->d_tables, tables.data(), tables.size() * sizeof(int));
+  // the default bank's weights also go to constant memory (identical for every frontend with that structure)
+  if (e == cudaSuccess && fe->default_bank) e = cudaMemcpyToSymbol(c_binw, binw.data(), kMaxBins * sizeof(float2));
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(logmel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelSmem);
+    e = cudaFuncSetAttribute(logmel_power_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(logmel_power_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelSmem);
   cudaDeviceProp prop;
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) {
     fe->num_sms = prop.multiProcessorCount;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fe->occupancy, logmel_power_kernel, kThreads, kLogmelSmem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fe->occupancy, logmel_power_kernel<true>, kThreads, kLogmelSmem);
   }
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
@@ -537,6 +668,8 @@ extern "C" int koe_frontend_destroy(koe_frontend_t* fe) {
   delete fe;
   return KOE_OK;
 }
+
+extern "C" int koe_frontend_uses_unrolled_bank(const koe_frontend_t* fe) { return fe != nullptr && fe->default_bank ? 1 : 0; }
 
 extern "C" int koe_frontend_filterbank_host(const koe_frontend_t* fe, float* fb_host) {
   KOE_REQUIRE(fe != nullptr && fb_host != nullptr, "koe_frontend_filterbank_host: NULL argument");
@@ -568,9 +701,10 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
   tab.hann = fe->d_hann;
   tab.tw = fe->d_tw;
   tab.binw = fe->d_binw;
-  tab.binkf = fe->d_tables;
-  tab.runs = fe->d_tables + kMaxBins;
+  tab.groups = reinterpret_cast<const int4*>(fe->d_tables);
+  tab.runs = fe->d_tables + 4 * kMaxGroups;
   tab.n_bins = fe->n_bins;
+  tab.n_groups = fe->n_groups;
   LogmelParams p;
   p.audio = a->audio;
   p.audio_stride = a->audio_stride;
@@ -589,10 +723,14 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
   p.power_clip_stride = a->power_clip_stride;
   p.fmax_clip_stride = a->frame_max_clip_stride;
   const long long ppc = (a->n_frames + 1) / 2;
+  KOE_REQUIRE((long long)a->n_clips * ppc < (1ll << 31) - kWarps, "koe_logmel_power: more than 2^31 frame pairs in one call");
   const long long n_blocks = ((long long)a->n_clips * ppc + kWarps - 1) / kWarps;
   const long long max_grid = (long long)fe->num_sms * fe->occupancy;
   const int grid = (int)std::min(n_blocks, max_grid);
-  logmel_power_kernel<<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
+  if (fe->default_bank)
+    logmel_power_kernel<true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
+  else
+    logmel_power_kernel<false><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
   count_launch();
   KOE_CUDA(cudaGetLastError());
   return KOE_OK;
