@@ -51,6 +51,10 @@ __global__ void __launch_bounds__(256) bench(float* out, int iters, float seed) 
     asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p[k]) : "f"(s[k]), "f"(s[k] + 1.0f));
   }
   int idx = threadIdx.x & 31;
+  int ix[kChains];
+  const int r0 = __float_as_int(seed) | 5, r1 = (int)(seed * 1e6f) | 3;
+#pragma unroll
+  for (int k = 0; k < kChains; ++k) ix[k] = threadIdx.x + k;
   float lacc = 0.f;
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -65,12 +69,17 @@ __global__ void __launch_bounds__(256) bench(float* out, int iters, float seed) 
         if (MODE == 5) { s[k] = ffma1(s[k], b, c); p[k] = ffma2(p[k], pb, pc); }   // 1 FFMA + 1 FFMA2
         if (MODE == 6) { p[k] = ffma2(p[k], pb, pc); lacc += sm[(idx + 32 * k + j) & 1023]; }  // FFMA2 + LDS + FADD
         if (MODE == 7) { s[k] = ffma1(s[k], b, c); lacc += sm[(idx + 32 * k + j) & 1023]; }    // FFMA + LDS + FADD
-        if (MODE == 8) { p[k] = ffma2(p[k], pb, pc); idx = (idx * 5 + k) & 1023; }            // FFMA2 + 2 int
-        if (MODE == 9) { s[k] = ffma1(s[k], b, c); idx = (idx * 5 + k) & 1023; }              // FFMA + 2 int
+        if (MODE == 8) { p[k] = ffma2(p[k], pb, pc); ix[k] = (ix[k] ^ r0) + r1; }                     // FFMA2 + 2 ALU (LOP3, IADD3)
+        if (MODE == 9) { s[k] = ffma1(s[k], b, c); ix[k] = (ix[k] ^ r0) + r1; }                       // FFMA + 2 ALU
+        if (MODE == 10) { p[k] = ffma2(p[k], pb, pc); ix[k] = ix[k] ^ (ix[k] >> 3); }                  // FFMA2 + 1 ALU (LOP3 w/ shift = SHF+LOP3?)
+        if (MODE == 11) { p[k] = ffma2(p[k], pb, pc); ix[k] = __vimax3_s32(ix[k], r0, r1) + 1; }       // FFMA2 + 1-2 ALU
+        if (MODE == 12) { ix[k] = (ix[k] ^ r0) + r1; }                                                 // 2 ALU only
       }
     }
   }
   float r = lacc + idx;
+#pragma unroll
+  for (int k = 0; k < kChains; ++k) r += ix[k];
 #pragma unroll
   for (int k = 0; k < kChains; ++k) {
     float lo, hi;
@@ -114,8 +123,11 @@ int main() {
   run<5>("FFMA + FFMA2", sms, d_out, 3);
   run<6>("FFMA2 + LDS + FADD", sms, d_out, 2);
   run<7>("FFMA + LDS + FADD", sms, d_out, 1);
-  run<8>("FFMA2 + IMAD + LOP3", sms, d_out, 2);
-  run<9>("FFMA + IMAD + LOP3", sms, d_out, 1);
+  run<8>("FFMA2 + LOP3 + IADD3", sms, d_out, 2);
+  run<9>("FFMA + LOP3 + IADD3", sms, d_out, 1);
+  run<10>("FFMA2 + SHF/LOP3", sms, d_out, 2);
+  run<11>("FFMA2 + VIMNMX3 + IADD", sms, d_out, 2);
+  run<12>("LOP3 + IADD3 only", sms, d_out, 0);
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
