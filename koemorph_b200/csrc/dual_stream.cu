@@ -320,13 +320,15 @@ __global__ void __launch_bounds__(kCoreThreads, 1) dual_stream_fp32_kernel(CoreP
   }
 }
 
-// ---- emotion stream: 16 clips per CTA, weights streamed through shared memory in 64-row cp.async chunks ----------
-constexpr int kEmoClips = 16;
+// ---- emotion stream: NC clips per CTA (16 for large batches, 4 when that leaves most SMs idle), weights streamed
+// through shared memory in 64-row cp.async chunks
+constexpr int kEmoClipsMax = 16;
 constexpr int kEmoInMax = 272;
 constexpr int kEmoChunkRows = 64;
 constexpr int kEmoBufFloats = kEmoChunkRows * kD;   // one chunk buffer: 64 rows of up to 256 floats (64 KB)
-constexpr size_t kEmoSmem = sizeof(float) * (2 * kEmoBufFloats + kEmoInMax * kEmoClips + kD * kEmoClips + 16 * 8 + 32);
+constexpr size_t kEmoSmem = sizeof(float) * (2 * kEmoBufFloats + kEmoInMax * kEmoClipsMax + kD * kEmoClipsMax + 16 * 8 + 32);
 
+template <int kEmoClips>
 __global__ void __launch_bounds__(256) emotion_stream_kernel(koe_core_weights W, const float* __restrict__ emo_in,
                                                              int n_clips, float* __restrict__ expr_sigmoid) {
   extern __shared__ __align__(16) float esm[];
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(256) emotion_stream_kernel(koe_core_weights W,
       const float w = wb[k * kD];
       const float4* xr = reinterpret_cast<const float4*>(s_x + (r0 + k) * kEmoClips);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < kEmoClips / 4; ++q) {
         const float4 x = xr[q];
         z[4 * q + 0] = fmaf(w, x.x, z[4 * q + 0]);
         z[4 * q + 1] = fmaf(w, x.y, z[4 * q + 1]);
@@ -440,14 +442,21 @@ __global__ void __launch_bounds__(256) emotion_stream_kernel(koe_core_weights W,
 #pragma unroll 4
     for (int k = 0; k < kEmoChunkRows; ++k) {
       const float w = wb[k * 128];
-      const float4* zr = reinterpret_cast<const float4*>(s_z + (r0 + k) * kEmoClips + half * (kEmoClips / 2));
+      const float* zr = s_z + (r0 + k) * kEmoClips + half * (kEmoClips / 2);
+      if constexpr (kEmoClips / 2 >= 4) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const float4 x = zr[q];
-        h[4 * q + 0] = fmaf(w, x.x, h[4 * q + 0]);
-        h[4 * q + 1] = fmaf(w, x.y, h[4 * q + 1]);
-        h[4 * q + 2] = fmaf(w, x.z, h[4 * q + 2]);
-        h[4 * q + 3] = fmaf(w, x.w, h[4 * q + 3]);
+        for (int q = 0; q < kEmoClips / 8; ++q) {
+          const float4 x = reinterpret_cast<const float4*>(zr)[q];
+          h[4 * q + 0] = fmaf(w, x.x, h[4 * q + 0]);
+          h[4 * q + 1] = fmaf(w, x.y, h[4 * q + 1]);
+          h[4 * q + 2] = fmaf(w, x.z, h[4 * q + 2]);
+          h[4 * q + 3] = fmaf(w, x.w, h[4 * q + 3]);
+        }
+      } else {
+        static_assert(kEmoClips / 2 == 2, "clips per half: 2 or a multiple of 4");
+        const float2 x = *reinterpret_cast<const float2*>(zr);
+        h[0] = fmaf(w, x.x, h[0]);
+        h[1] = fmaf(w, x.y, h[1]);
       }
     }
     __syncthreads();
@@ -552,16 +561,20 @@ extern "C" int koe_emotion_stream(const koe_core_weights* w, const float* emo_in
   if (int rc = validate_weights(w)) return rc;
   KOE_REQUIRE(emo_in != nullptr && expr_sigmoid != nullptr && n_clips >= 0, "koe_emotion_stream: bad argument");
   if (n_clips == 0) return KOE_OK;
-  const int grid = (n_clips + kEmoClips - 1) / kEmoClips;
   static bool configured[64] = {false};
   int dev = 0;
   KOE_CUDA(cudaGetDevice(&dev));
   KOE_REQUIRE(dev >= 0 && dev < 64, "device index too large");
   if (!configured[dev]) {
-    KOE_CUDA(cudaFuncSetAttribute(emotion_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmoSmem));
+    KOE_CUDA(cudaFuncSetAttribute(emotion_stream_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmoSmem));
+    KOE_CUDA(cudaFuncSetAttribute(emotion_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmoSmem));
     configured[dev] = true;
   }
-  emotion_stream_kernel<<<grid, 256, kEmoSmem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
+  // every CTA streams all the weights (0.4 MB, L2 resident): few clips per CTA while that keeps the grid within ~4 waves
+  if (n_clips <= 4 * 600)
+    emotion_stream_kernel<4><<<(n_clips + 3) / 4, 256, kEmoSmem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
+  else
+    emotion_stream_kernel<16><<<(n_clips + 15) / 16, 256, kEmoSmem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
   count_launch();
   KOE_CUDA(cudaGetLastError());
   return KOE_OK;
