@@ -246,6 +246,28 @@ def run_gpu(args):
     elapsed_ms = float(tt.item())
     value = world * B * CLIP_SECONDS * args.steps / (elapsed_ms * 1e-3)
 
+    # ---- the other precision of BASELINE.json configs[1] ("fp32 and bf16"), same workload, device-resident, fewer steps ----
+    other = None
+    if not args.no_other_precision:
+        other_name = "bf16" if args.precision == "fp32" else "fp32"
+        model.precision = other_name
+        for _ in range(3):
+            step(False)
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_other = max(3, min(args.steps, 20))
+        o0.record()
+        for _ in range(n_other):
+            step(False)
+        o1.record()
+        barrier()
+        to = torch.tensor([o0.elapsed_time(o1)], device=dev)
+        if world > 1:
+            dist.all_reduce(to, op=dist.ReduceOp.MAX)
+        other = {"precision": other_name, "value": world * B * CLIP_SECONDS * n_other / (float(to.item()) * 1e-3),
+                 "unit": UNIT, "ms_per_step": float(to.item()) / n_other, "steps": n_other}
+        model.precision = args.precision
+
     # ---- end to end through the host-buffer API (pinned host -> H2D -> kernels -> D2H) ----
     e2e_value, e2e_steps = None, 0
     if not args.no_e2e:
@@ -310,6 +332,8 @@ def run_gpu(args):
                          "peak_source": peak_src, "kernel_ms": k1_ms, "share_of_step": k1_ms / (elapsed_ms / args.steps),
                          "algorithmic_bytes_per_launch": k1_bytes},
         }
+        if other is not None:
+            line["other_precision"] = other
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
@@ -326,6 +350,7 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--no-other-precision", action="store_true", help="skip the secondary (bf16 / fp32) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -58,6 +58,7 @@ _SIGNATURES = {
                                       C.POINTER(C.c_void_p)]),
     "koe_frontend_destroy": (C.c_int, [C.c_void_p]),
     "koe_frontend_filterbank_host": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "koe_frontend_uses_unrolled_bank": (C.c_int, [C.c_void_p]),
     "koe_logmel_power": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "koe_logmel_power_ex": (C.c_int, [C.c_void_p, C.POINTER(LogmelArgs), C.c_void_p]),

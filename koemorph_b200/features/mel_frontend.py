@@ -53,6 +53,11 @@ class LogMelFrontend:
         except Exception:
             pass
 
+    def uses_unrolled_bank(self) -> bool:
+        """True when this bank has the structure of the path's default (sr 16000, 80 mels, 80..8000 Hz) and the kernel
+        runs the filterbank phase unrolled from it; False: generic looped kernel (same results, slower)."""
+        return bool(self._lib.koe_frontend_uses_unrolled_bank(self._h))
+
     def filterbank(self) -> np.ndarray:
         fb = np.empty((self.n_mels, 1 + self.n_fft // 2), np.float32)
         _lib.check(self._lib.koe_frontend_filterbank_host(self._h, fb.ctypes.data_as(C.c_void_p)))

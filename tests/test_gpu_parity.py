@@ -65,6 +65,27 @@ def test_filterbank_matches_oracle(K):
     assert ((fb > 0) == (ref > 0)).all()
 
 
+def test_default_bank_is_unrolled_and_generic_bank_agrees(K):
+    """The path's filterbank takes the unrolled kernel (a silent fall-back to the generic loops would only show up as a
+    slower bench); a bank with other band edges takes the generic kernel, and both agree with the float64 oracle."""
+    from koemorph_b200.features.mel_frontend import LogMelFrontend
+    assert LogMelFrontend.get("cuda").uses_unrolled_bank()
+    other = LogMelFrontend.get("cuda", f_min=60.0, f_max=7600.0)
+    assert not other.uses_unrolled_bank()
+    audio, _ = O.make_inputs(77, 2, 40000, "speechlike")
+    for fe, (fmin, fmax) in ((LogMelFrontend.get("cuda"), (80.0, 8000.0)), (other, (60.0, 7600.0))):
+        db, fmx = fe.power(torch.from_numpy(audio).cuda(), 533, 76)
+        db = db.cpu().double().numpy()
+        fb = O.mel_filterbank(fmin=fmin, fmax=fmax).astype(np.float64)
+        assert np.abs(fe.filterbank() - fb).max() <= 1.2e-7 * fb.max()
+        for b in range(2):
+            spec = np.abs(O.stft(audio[b], hop_length=533, exact=True)) ** 2
+            ref = (fb @ spec).T
+            big = ref > 1e-6 * ref.max()
+            assert np.abs(db[b] - 10 * np.log10(np.maximum(ref, 1e-10)))[big].max() < 8.7e-4
+            np.testing.assert_allclose(fmx[b].cpu().numpy(), db[b].max(axis=1), rtol=1e-6)
+
+
 @pytest.mark.parametrize("name", SINGLE)
 def test_logmel_vs_golden(K, golden, name):
     cases, data = golden
