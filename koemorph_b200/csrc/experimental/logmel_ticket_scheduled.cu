@@ -1,26 +1,39 @@
+// EXPERIMENT -- NOT BUILT, NOT SHIPPED.  Barrier-free variant of logmel.cu kept for the record (round 1): 16 identical
+// warps; frame pairs, filterbank tasks and store tasks handed out by tickets; dependencies as release / acquire counters
+// with "helping" waits.  Parity: identical results to logmel.cu (scripts/k1_check.py).
+// Measured on B200, 512 clips x 257 frames: 268 us against 222-226 us for the lock-step kernel in ../logmel.cu.
+// Why it lost (ncu source counters, profiles/ncu_k1_r01_experiment_ticket_scheduled_summary.txt): the kernel is ~5400
+// SASS instructions (87 KB) of straight-line code; once the warps drift apart each one streams its own instructions and
+// "no instruction" becomes the second largest stall (19 %), where the lock-step kernel keeps all 16 warps within the same
+// few cache lines of the unrolled FFT.  It needs melbank_default_16runs.inc (WARPS = 16 and baked weights).
+//
 // Log-mel frontend for sm_100a: framing + periodic Hann + 1024-point FFT + |X|^2 + sparse Slaney
 // filterbank, fused in one kernel; then a small dB-normalisation kernel.
 //
 // Replaces the per-clip librosa loop of SimplifiedDualStreamModel.extract_mel_features
 // (reference src/model/simplified_dual_stream_model.py:184-229).
 //
-// Kernel design (see DESIGN.md section "K1"):
-//   * one warp transforms TWO real frames of the same clip at once as one complex 1024-point FFT
-//     (z = a + i b), decomposed 32 x 32: radix-2 DIT FFT of 32 points in registers, twiddle, 32x32 transpose
-//     through a padded shared-memory tile, second 32-point FFT in registers.  Every complex value is one
-//     64-bit register pair and every butterfly is written with the packed fp32x2 instructions of sm_100
-//     (FADD2 / FMUL2 / FFMA2, whose operands take per-half negation and a half swap, so "times -i" is free
-//     and a butterfly with a general twiddle is 3 instructions: x = a + w b as two FFMA2, y = 2a - x as one).
-//   * after the second pass lane l holds Z[l + 32 r]; the conjugate-symmetric partner Z[1024 - k] lives in lane
-//     (32 - l) & 31, so the two real spectra are separated with 32 warp shuffles and no further shared-memory
-//     round trip; the pair (|A_k|^2, |B_k|^2) comes out of one FMUL2 + one FFMA2.
-//   * a CTA is 16 warps (register-limited: one CTA per SM) -> 32 power spectra per iteration, parked in the warps'
-//     transposition tiles with bank-skewed bases.  The Slaney filterbank is then applied with lane = frame: the 16
-//     warps split the filter groups, every weight / bin index is a broadcast, every spectrum read is conflict-free
-//     and the control flow is warp-uniform.
-//   * results leave through a shared staging tile as coalesced rows of 80 mel values in dB.
-//   * the audio of the NEXT iteration is loaded into registers before the filterbank phase, so DRAM latency
-//     hides behind it.
+// Kernel design (see DESIGN.md section "K1"): one persistent CTA of 16 identical warps per SM (128 registers per thread
+// allow no more), no CTA-wide barrier in the main loop.
+//   * FFT: a warp transforms TWO real frames of one clip at once as one complex 1024-point FFT (z = a + i b), decomposed
+//     32 x 32: radix-2 DIT FFT of 32 points in registers, twiddle, 32x32 transpose through a padded shared-memory slot
+//     (real plane, then imaginary plane), second 32-point FFT in registers.  Every complex value is one 64-bit register
+//     pair and every butterfly is written with the packed fp32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2, whose
+//     operands take per-half negation and a half swap, so "times -i" is free and a butterfly with a general twiddle is 3
+//     instructions: x = a + w b as two FFMA2, y = 2a - x as one).  After the second pass lane l holds Z[l + 32 r]; the
+//     conjugate-symmetric partner Z[1024 - k] lives in lane (32 - l) & 31, so the two real spectra are separated with 32
+//     warp shuffles; the pair (|A_k|^2, |B_k|^2) comes out of one FMUL2 + one FFMA2 and is parked in the slot.
+//   * Filterbank: lane = frame.  Sixteen frame pairs form a batch (32 frames = 32 lanes); the Slaney filterbank of a batch
+//     is cut into 16 tasks (runs of bins), each straight-line code unrolled from the bank's compile-time tables
+//     (melbank_default.inc: immediate weights, conflict-free LDS.128 of four bins, warp-uniform control flow).
+//   * Rows: 16 store tasks per batch convert two rows of 80 sums to dB and write them, with the per-frame maximum.
+//   * Scheduling: frame pairs, filterbank tasks and store tasks are handed out by tickets (shared-memory counters) to
+//     whichever warp is free -- the SM sub-partitions arbitrate by warp id, so warps run at persistently different
+//     speeds and any fixed assignment would wait for the slowest.  Dependencies (batch complete -> filterbank; filterbank
+//     complete -> rows, slot reuse two batches later; rows stored -> tile reuse) are monotonic counters with
+//     release / acquire semantics, and every wait "helps": it executes pending filterbank / store tasks instead of idling,
+//     which also makes the scheme deadlock-free.  The audio of a warp's next pair is loaded into registers before it
+//     turns to filterbank / store tasks, so DRAM latency hides behind them.
 #include <algorithm>
 #include <cmath>
 #include <mutex>
@@ -34,14 +47,18 @@ constexpr int kFrameLen = 1024;
 constexpr int kBins = 513;
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr int kSlots = 2 * kWarps;      // frames per CTA iteration (= 32: one per lane in the filterbank phase)
-constexpr int kRowF2 = 33;              // float2 per row of the transposition tile (padded: conflict-free both ways)
-constexpr int kScratch = 2120;          // floats per warp tile: >= 2 * 32 * 33, == 8 (mod 32)
-constexpr int kSecondFrame = 516;       // offset of the warp's second spectrum, == 4 (mod 32): with lane = frame the
-                                        // bases of 8 consecutive frames are 16 bytes apart mod 128 -> LDS.128 conflict-free
-constexpr int kMaxBins = 512;           // spectrum bins that carry filterbank weight (507 for 80..8000 Hz)
+constexpr int kBatchPairs = 16;         // frame pairs per batch: 32 frames = one lane each in the filterbank tasks
+constexpr int kRow = 33;                // floats per row of the transposition slot (padded: conflict-free both ways)
+constexpr int kSlotFloats = 32 * kRow;  // 1056 floats: one plane of the 32x32 transpose, then the two power spectra
+constexpr int kSecondFrame = 516;       // offset of the second spectrum, == 4 (mod 32)
+constexpr int kPosStride = 2 * kSlotFloats + 8;  // two slots (batch parity) per batch position; == 8 (mod 32) floats: with
+                                        // lane = frame the bases of 8 consecutive frames are 16 bytes apart mod 128
+                                        // -> the filterbank's LDS.128 are conflict-free
+constexpr int kMaxBins = 512;           // spectrum bins that carry filterbank weight (506 for 80..8000 Hz)
 constexpr int kMaxGroups = 96;          // groups of consecutive bins feeding the same pair of adjacent filters
-constexpr int kTileStride = 81;         // mel staging row stride (floats), odd: conflict-free across frames
+constexpr int kTileStride = 81;         // filterbank tile row stride (floats), odd: conflict-free across frames
+constexpr int kTileFloats = 2 * kBatchPairs * kTileStride;  // one tile: 32 rows
+static_assert(kPosStride % 32 == 8 && kSecondFrame % 32 == 4 && kSecondFrame + kBins <= kSlotFloats, "bank skew / slot size");
 
 struct FrontendTables {
   const float* hann;     // [1024]
@@ -49,7 +66,7 @@ struct FrontendTables {
   // Slaney filterbank, bin-major: a spectrum bin feeds at most two ADJACENT filters (fl, fl + 1)
   const float2* binw;    // [n_bins] 0.25 * (weight into filter fl, weight into filter fl + 1)
   const int4* groups;    // [n_groups] {first bin k, first entry of binw, number of bins, fl}: fl rises by one per group
-  const int* runs;       // [kWarps + 1] group range of every warp in the filterbank phase
+  const int* runs;       // [kBatchPairs + 1] group range of every filterbank task (generic bank)
   int n_bins, n_groups;
 };
 
@@ -135,14 +152,15 @@ struct PairInfo {
   bool interior, has_b;
 };
 
-__device__ __forceinline__ PairInfo locate_pair(const LogmelParams& p, unsigned pair, unsigned total_pairs, unsigned ppc) {
+// pair number `pic` of clip `b` (frames 2 pic, 2 pic + 1); b >= n_clips: no pair
+__device__ __forceinline__ PairInfo describe_pair(const LogmelParams& p, int b, int pic) {
   PairInfo pi;
   pi.clip = 0;
   pi.frame = -1;
   pi.interior = false;
-  if (pair >= total_pairs) return pi;
-  const int b = (int)(pair / ppc);
-  const int ga = 2 * (int)(pair - (unsigned)b * ppc);
+  pi.has_b = false;
+  if (b >= p.n_clips) return pi;
+  const int ga = 2 * pic;
   pi.clip = b;
   pi.frame = ga;
   pi.has_b = ga + 1 < p.n_frames;
@@ -164,6 +182,23 @@ __device__ __forceinline__ PairInfo locate_pair(const LogmelParams& p, unsigned 
   return pi;
 }
 
+// A warp's position in the pair sequence, advanced without divisions: every batch moves it by the same number of pairs.
+struct PairCursor {
+  int clip, pic;
+  __device__ __forceinline__ void init(unsigned pair, unsigned ppc) {
+    clip = (int)(pair / ppc);
+    pic = (int)(pair - (unsigned)clip * ppc);
+  }
+  __device__ __forceinline__ void advance(int dclip, int dpic, int ppc) {
+    clip += dclip;
+    pic += dpic;
+    while (pic >= ppc) {  // (one turn, unless a clip has fewer pairs than the step)
+      pic -= ppc;
+      ++clip;
+    }
+  }
+};
+
 // interior frames (all but the first / last of a clip): no masking.  v[bitrev5(n1)] = (a[32 n1 + lane], b[32 n1 + lane])
 __device__ __forceinline__ void load_interior(const LogmelParams& p, const PairInfo& pi, int lane, float2 (&v)[32]) {
   const float* clip = p.audio + (long long)pi.clip * p.audio_stride;
@@ -173,14 +208,15 @@ __device__ __forceinline__ void load_interior(const LogmelParams& p, const PairI
   for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = make_float2(__ldg(pa + 32 * n1), __ldg(pb + 32 * n1));
 }
 
-// frames that touch a clip / window edge (~2 pairs per clip): masked or reflected samples, staged through the warp's
-// shared-memory tile as tile[n1 * 32 + lane] = (a, b); out of line and not unrolled to keep the hot loop small
+// frames that touch a clip / window edge (~2 pairs per clip): masked or reflected samples, staged through the pair's
+// spectrum slot sixteen rows at a time as tile[(n1 - n1_begin) * 32 + lane] = (a, b); out of line and not unrolled to
+// keep the hot loop small
 __device__ __noinline__ void load_edge(const float* __restrict__ clip, int n_samples, int pad_mode, int fa_lo, int fb_lo,
-                                       int lo_a, int hi_a, int lo_b, int hi_b, float2* tile) {
+                                       int lo_a, int hi_a, int lo_b, int hi_b, float2* tile, int n1_begin) {
   const int lane = threadIdx.x & 31;
   const int last = n_samples - 1;
 #pragma unroll 1
-  for (int n1 = 0; n1 < 32; ++n1) {
+  for (int n1 = n1_begin; n1 < n1_begin + 16; ++n1) {
     int sa = fa_lo + lane + 32 * n1, sb = fb_lo + lane + 32 * n1;
     bool oka, okb;
     if (pad_mode == 1) {  // numpy "reflect" padding about the first / last sample (MelSlidingWindowExtractor default)
@@ -192,7 +228,7 @@ __device__ __noinline__ void load_edge(const float* __restrict__ clip, int n_sam
       oka = sa >= lo_a && sa < hi_a;
       okb = sb >= lo_b && sb < hi_b;
     }
-    tile[n1 * 32 + lane] = make_float2(oka ? __ldg(clip + sa) : 0.0f, okb ? __ldg(clip + sb) : 0.0f);
+    tile[(n1 - n1_begin) * 32 + lane] = make_float2(oka ? __ldg(clip + sa) : 0.0f, okb ? __ldg(clip + sb) : 0.0f);
   }
 }
 
@@ -207,11 +243,12 @@ __device__ __forceinline__ int float_order(float f) {
 }
 __device__ __forceinline__ float order_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-// ---- filterbank phase, default bank: straight-line code from the compile-time tables ------------------------------
+// ---- filterbank tasks, default bank: straight-line code from the compile-time tables -------------------------------
 #include "melbank_default.inc"
+
 // Bins [b0, b1) of run W for one spectrum (lane = frame): every bin feeds the falling half of filter g (-> tlo[g]) and
-// the rising half of filter g + 1 (-> thi[g + 1]) with immediate weights (kDefBinWDev folds away after unrolling); two
-// accumulator pairs alternate so that the FFMA chains are half as long.
+// the rising half of filter g + 1 (-> thi[g + 1]) with immediate weights; two accumulator pairs alternate so that the
+// FFMA chains are half as long.  Runs are cut between groups, so every (tile, filter) cell has exactly one writer.
 template <int W>
 __device__ __forceinline__ void mel_run_default(const float* __restrict__ spec, float* __restrict__ tlo,
                                                 float* __restrict__ thi) {
@@ -226,7 +263,7 @@ __device__ __forceinline__ void mel_run_default(const float* __restrict__ spec, 
     for (int j = 0; j < 4; ++j) {
       const int k = k4 + j;
       if (k >= b0 && k < b1) {
-        if (k > b0 && kDefBinGroupDev[k] != kDefBinGroupDev[k - 1]) {  // next interval: retire the falling / rising halves
+        if (k > b0 && kDefBinGroupDev[k] != kDefBinGroupDev[k - 1]) {  // next interval: retire the two halves
           tlo[kDefBinGroupDev[k - 1]] = lo0 + lo1;
           thi[kDefBinGroupDev[k - 1] + 1] = hi0 + hi1;
           lo0 = lo1 = hi0 = hi1 = 0.0f;
@@ -246,8 +283,9 @@ __device__ __forceinline__ void mel_run_default(const float* __restrict__ spec, 
   thi[kDefBinGroupDev[b1 - 1] + 1] = hi0 + hi1;  // the rising half of "filter 80" lands in the spare column of the tile
 }
 
-__device__ __forceinline__ void mel_phase_default(int warp, const float* spec, float* tlo, float* thi) {
-  switch (warp) {
+__device__ __noinline__ void mel_task_default(int run, const float* spec, float* tlo, float* thi) {
+  static_assert(kBatchPairs == 16, "melbank_default.inc is generated for sixteen filterbank tasks");
+  switch (run) {
     case 0: mel_run_default<0>(spec, tlo, thi); break;
     case 1: mel_run_default<1>(spec, tlo, thi); break;
     case 2: mel_run_default<2>(spec, tlo, thi); break;
@@ -268,8 +306,8 @@ __device__ __forceinline__ void mel_phase_default(int warp, const float* spec, f
 }
 
 // generic bank (any other sample rate / band edges): warp-uniform loops over the group table
-__device__ __forceinline__ void mel_phase_generic(int g, int gend, const int4* s_groups, const float2* s_binw,
-                                                  const float* spec, float* tlo, float* thi) {
+__device__ __noinline__ void mel_task_generic(int g, int gend, const int4* s_groups, const float2* s_binw,
+                                              const float* spec, float* tlo, float* thi) {
   for (; g < gend; ++g) {
     const int4 gi = s_groups[g];
     const float* x = spec + gi.x;
@@ -286,160 +324,295 @@ __device__ __forceinline__ void mel_phase_generic(int g, int gend, const int4* s
   }
 }
 
+// ---- progress counters in shared memory (monotonic, release / acquire at CTA scope) -----------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned load_acquire(const unsigned* counter) {
+  unsigned seen;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_addr(counter)) : "memory");
+  return seen;
+}
+__device__ __forceinline__ void add_release(unsigned* counter) {  // this thread's (and, after __syncwarp, its warp's) writes first
+  asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(smem_addr(counter)) : "memory");
+}
+// counters are per batch parity and advance by kBatchPairs per batch: batch b is through when its counter reaches this
+__device__ __forceinline__ unsigned batch_goal(unsigned b) { return kBatchPairs * ((b >> 1) + 1); }
+
+struct Counters {
+  unsigned fft_ticket, mel_ticket, store_ticket, pad_;
+  unsigned arrived[2];   // frame pairs whose spectra are in their slot
+  unsigned mel_done[2];  // filterbank tasks finished
+  unsigned stored[2];    // store tasks finished
+};
+constexpr int kSmemCounterBytes = 256;
+
+// One frame pair after the windowed samples are in v: transform_first = FFT, twiddle; transform_second =
+// transpose, FFT, separation, which leaves 4 |A_k|^2 at slot[k] and 4 |B_k|^2 at slot[kSecondFrame + k], k = 0..512.
+__device__ __forceinline__ void transform_first(float2 (&v)[32], const float2* s_tw, int lane) {
+  fft32(v);  // v[k1] = Y[k1] of column n2 = lane
+#pragma unroll
+  for (int k1 = 1; k1 < 32; ++k1) {
+    const float2 w = s_tw[k1 * 32 + lane];  // W_1024^(k1 * n2)
+    const float2 z = v[k1];
+    float2 r = __fmul2_rn(z, bcast(w.x));
+    v[k1] = __ffma2_rn(make_float2(-z.y, z.x), bcast(w.y), r);
+  }
+}
+
+__device__ __forceinline__ void transform_second(float2 (&v)[32], float* slot, int lane) {
+  // 32x32 transpose through the padded slot, real plane then imaginary plane (the slot is sized for one plane: two slots
+  // per batch position leave the rest of shared memory to L1, which serves the 48 % overlap of consecutive frames)
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) slot[k1 * kRow + lane] = v[k1].x;
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) v[bitrev5(n2)].x = slot[lane * kRow + n2];  // (.y still holds the old imaginary parts)
+  __syncwarp();
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) slot[k1 * kRow + lane] = v[k1].y;
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) v[bitrev5(n2)].y = slot[lane * kRow + n2];
+  __syncwarp();
+  fft32(v);  // v[k2] = Z[lane + 32 * k2]
+
+  // separate the two real spectra: partner of k = lane + 32 r is 1024 - k = ((32-lane)&31) + 32 r'.
+  // Lanes 1..31: partner register r' = 31 - r; lane 0: r' = 32 - r, which is the value it fetched (from itself) one step
+  // earlier, and r = 0 is its own partner.  Four steps at a time, so that only 8 shuffle results are live at once.
+  const int src = (32 - lane) & 31;
+  float* pa = slot;
+  float* pb = slot + kSecondFrame;
+  float2 prev = v[0];
+#pragma unroll
+  for (int r0 = 0; r0 < 16; r0 += 4) {
+    float2 q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[j].x = __shfl_sync(kFullMask, v[31 - r0 - j].x, src);
+      q[j].y = __shfl_sync(kFullMask, v[31 - r0 - j].y, src);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + j;
+      const float2 z = v[r];
+      const float2 c = lane == 0 ? prev : q[j];
+      prev = q[j];
+      // 2A = z + conj(c), 2iB = z - conj(c): (4|A|^2, 4|B|^2) = u*u + w*w, u = (z.x + c.x, z.x - c.x), w = (z.y - c.y, z.y + c.y)
+      const float2 u = __fadd2_rn(bcast(z.x), make_float2(c.x, -c.x));
+      const float2 w = __fadd2_rn(bcast(z.y), make_float2(-c.y, c.y));
+      const float2 pw = __ffma2_rn(w, w, __fmul2_rn(u, u));
+      pa[lane + 32 * r] = pw.x;
+      pb[lane + 32 * r] = pw.y;
+    }
+    asm volatile("" ::: "memory");  // keep the compiler from hoisting the next group's shuffles (register pressure)
+  }
+  if (lane == 0) {  // Nyquist bin 512 = register 16, self-paired: A = z.x, B = z.y (x4 like the others)
+    pa[512] = 4.0f * v[16].x * v[16].x;
+    pb[512] = 4.0f * v[16].y * v[16].y;
+  }
+}
+
+// dB rows + per-frame max of one frame pair from the filterbank tile (rows 2 * position, 2 * position + 1 of the two halves)
+__device__ __forceinline__ void store_pair(const LogmelParams& p, const PairInfo& pi, const float* tlo, const float* thi,
+                                           int lane) {
+  float* dst = p.power + (long long)pi.clip * p.power_clip_stride + (long long)pi.frame * KOE_N_MELS;
+  // the 160 values of the two rows (row B follows row A in the clip's block), five per lane: j = lane + 32 q;
+  // j < 80 -> frame A filter j, else frame B filter j - 80, which sits kTileStride - 80 = 1 float further in the tile
+  float db[5];
+#pragma unroll
+  for (int qd = 0; qd < 5; ++qd) {
+    const int j = lane + 32 * qd;
+    const bool second = qd > 2 || (qd == 2 && lane >= KOE_N_MELS - 64);
+    const int t = j + (second ? kTileStride - KOE_N_MELS : 0);
+    db[qd] = db_from_power(tlo[t] + thi[t]);  // stored in dB: the consumer of the buffer only subtracts its reference
+  }
+  float mx_a = fmaxf(db[0], db[1]), mx_b = fmaxf(db[3], db[4]);
+  if (lane < KOE_N_MELS - 64) mx_a = fmaxf(mx_a, db[2]); else mx_b = fmaxf(mx_b, db[2]);
+  dst[lane] = db[0];
+  dst[lane + 32] = db[1];
+  if (pi.has_b || lane < KOE_N_MELS - 64) dst[lane + 64] = db[2];
+  if (pi.has_b) {
+    dst[lane + 96] = db[3];
+    dst[lane + 128] = db[4];
+  }
+  if (p.frame_max != nullptr) {
+    const int ia = __reduce_max_sync(kFullMask, float_order(mx_a));
+    const int ib = __reduce_max_sync(kFullMask, float_order(mx_b));
+    float* fm = p.frame_max + (long long)pi.clip * p.fmax_clip_stride + pi.frame;
+    if (lane == 0) fm[0] = order_float(ia);
+    if (lane == 1 && pi.has_b) fm[1] = order_float(ib);
+  }
+}
+
 template <bool kDefaultBank>
 __global__ void __launch_bounds__(kThreads, 1)
 logmel_power_kernel(FrontendTables tab, LogmelParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* s_hann = reinterpret_cast<float*>(smem_raw);              // 1024
-  float2* s_tw = reinterpret_cast<float2*>(s_hann + kFrameLen);    // 1024 float2
-  float2* s_binw = s_tw + 1024;                                    // kMaxBins float2
-  int4* s_groups = reinterpret_cast<int4*>(s_binw + kMaxBins);     // kMaxGroups
-  int* s_runs = reinterpret_cast<int*>(s_groups + kMaxGroups);     // kWarps + 1 (+ pad to 32)
-  float* s_tlo = reinterpret_cast<float*>(s_runs + 32);            // kSlots * kTileStride: falling halves (filter g of group g)
-  float* s_thi = s_tlo + kSlots * kTileStride;                     // kSlots * kTileStride: rising halves (filter g + 1)
-  float* s_scratch = s_thi + kSlots * kTileStride;                 // kWarps * kScratch, 16-byte aligned, bank 0
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Counters* ctr = reinterpret_cast<Counters*>(smem_raw);
+  float* s_hann = reinterpret_cast<float*>(smem_raw + kSmemCounterBytes);     // 1024
+  float2* s_tw = reinterpret_cast<float2*>(s_hann + kFrameLen);               // 1024 float2
+  float2* s_binw = s_tw + 1024;                                               // kMaxBins float2 (generic bank)
+  int4* s_groups = reinterpret_cast<int4*>(s_binw + kMaxBins);                // kMaxGroups       (generic bank)
+  int* s_runs = reinterpret_cast<int*>(s_groups + kMaxGroups);                // kBatchPairs + 1 (+ pad to 32)
+  float* s_tlo = reinterpret_cast<float*>(s_runs + 32);                       // [2 parities][32 rows][81]: falling halves
+  float* s_thi = s_tlo + 2 * kTileFloats;                                     // [2 parities][32 rows][81]: rising halves
+  float* s_slots = s_thi + 2 * kTileFloats;                                   // kBatchPairs x (slot parity 0 | slot parity 1)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int i = tid; i < kFrameLen; i += kThreads) s_hann[i] = tab.hann[i];
   for (int i = tid; i < 1024; i += kThreads) s_tw[i] = tab.tw[i];
-  for (int i = tid; i < tab.n_bins; i += kThreads) s_binw[i] = tab.binw[i];
-  for (int i = tid; i < tab.n_groups; i += kThreads) s_groups[i] = tab.groups[i];
-  if (tid <= kWarps) s_runs[tid] = tab.runs[tid];
-  if (tid < kSlots) s_thi[tid * kTileStride] = 0.0f;  // filter 0 has no rising half from a lower interval
+  if (!kDefaultBank) {
+    for (int i = tid; i < tab.n_bins; i += kThreads) s_binw[i] = tab.binw[i];
+    for (int i = tid; i < tab.n_groups; i += kThreads) s_groups[i] = tab.groups[i];
+    if (tid <= kBatchPairs) s_runs[tid] = tab.runs[tid];
+  }
+  if (tid < 2 * 2 * kBatchPairs) s_thi[tid * kTileStride] = 0.0f;  // filter 0 has no rising half from a lower interval
+  if (tid < (int)(sizeof(Counters) / sizeof(unsigned))) reinterpret_cast<unsigned*>(ctr)[tid] = 0;
   __syncthreads();
 
   const unsigned ppc = (unsigned)(p.n_frames + 1) >> 1;  // frame pairs per clip
   const unsigned total_pairs = (unsigned)p.n_clips * ppc;
-  const unsigned n_iters = (total_pairs + kWarps - 1) / kWarps;
-  float* xb = s_scratch + warp * kScratch;
-  float2* xb2 = reinterpret_cast<float2*>(xb);
+  const unsigned n_batches = (total_pairs + kBatchPairs - 1) / kBatchPairs;
+  // this CTA's batches: blockIdx.x, blockIdx.x + gridDim.x, ...; its tickets number them 0, 1, ...
+  const unsigned my_batches = blockIdx.x < n_batches ? (n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const unsigned n_tickets = my_batches * kBatchPairs;  // of each kind: frame pairs, filterbank tasks, store tasks
 
-  float2 v[32];
-  unsigned it = blockIdx.x;
-  PairInfo nxt = locate_pair(p, it < n_iters ? it * kWarps + warp : total_pairs, total_pairs, ppc);
-  if (nxt.interior) load_interior(p, nxt, lane, v);
+  auto describe_ticket = [&](unsigned t) -> PairInfo {  // pair at position t % 16 of this CTA's batch t / 16
+    if (t >= n_tickets) return describe_pair(p, p.n_clips, 0);
+    const unsigned b = t / kBatchPairs, j = t - b * kBatchPairs;
+    PairCursor pos;
+    pos.init((blockIdx.x + b * gridDim.x) * kBatchPairs + j, ppc);
+    return describe_pair(p, pos.clip, pos.pic);
+  };
 
-  for (; it < n_iters; it += gridDim.x) {
-    // ------------------------------------------------------------------ FFT phase (per warp)
-    const PairInfo cur = nxt;
-    if (cur.frame >= 0) {
-      if (!cur.interior) {
-        load_edge(p.audio + (long long)cur.clip * p.audio_stride, p.n_samples, p.pad_mode, cur.fa_lo, cur.fb_lo, cur.lo_a,
-                  cur.hi_a, cur.lo_b, cur.hi_b, xb2);
-        __syncwarp();
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = xb2[n1 * 32 + lane];
-        __syncwarp();
+  // ---- filterbank / store tasks: taken by compare-and-swap only when their inputs are ready, so taking never blocks
+  auto try_mel_task = [&]() -> bool {
+    unsigned t = 0, ok = 0;
+    if (lane == 0) {
+      t = load_acquire(&ctr->mel_ticket);
+      if (t < n_tickets) {
+        const unsigned b = t / kBatchPairs;
+        // the batch's 32 spectra are in their slots, and the rows of the batch that used this tile before are stored
+        ok = load_acquire(&ctr->arrived[b & 1]) >= batch_goal(b) &&
+             (b < 2 || load_acquire(&ctr->stored[b & 1]) >= batch_goal(b - 2));
+        if (ok) ok = atomicCAS(&ctr->mel_ticket, t, t + 1) == t;
       }
+    }
+    ok = __shfl_sync(kFullMask, ok, 0);
+    if (!ok) return false;
+    t = __shfl_sync(kFullMask, t, 0);
+    const unsigned b = t / kBatchPairs, run = t - b * kBatchPairs;
+    const float* spec = s_slots + (lane >> 1) * kPosStride + (b & 1) * kSlotFloats + (lane & 1) * kSecondFrame;
+    float* tlo = s_tlo + ((b & 1) * 2 * kBatchPairs + lane) * kTileStride;
+    float* thi = s_thi + ((b & 1) * 2 * kBatchPairs + lane) * kTileStride;
+    if (kDefaultBank)
+      mel_task_default((int)run, spec, tlo, thi);
+    else
+      mel_task_generic(s_runs[run], s_runs[run + 1], s_groups, s_binw, spec, tlo, thi);
+    __syncwarp();
+    if (lane == 0) add_release(&ctr->mel_done[b & 1]);
+    return true;
+  };
+  auto try_store_task = [&]() -> bool {
+    unsigned t = 0, ok = 0;
+    if (lane == 0) {
+      t = load_acquire(&ctr->store_ticket);
+      if (t < n_tickets) {
+        const unsigned b = t / kBatchPairs;
+        ok = load_acquire(&ctr->mel_done[b & 1]) >= batch_goal(b);
+        if (ok) ok = atomicCAS(&ctr->store_ticket, t, t + 1) == t;
+      }
+    }
+    ok = __shfl_sync(kFullMask, ok, 0);
+    if (!ok) return false;
+    t = __shfl_sync(kFullMask, t, 0);
+    const unsigned b = t / kBatchPairs, j = t - b * kBatchPairs;
+    const PairInfo pi = describe_ticket(t);
+    if (pi.frame >= 0) {
+      const int row = ((b & 1) * 2 * kBatchPairs + 2 * j) * kTileStride;
+      store_pair(p, pi, s_tlo + row, s_thi + row, lane);
+    }
+    __syncwarp();
+    if (lane == 0) add_release(&ctr->stored[b & 1]);
+    return true;
+  };
+  // wait until the filterbank of batch b is complete (its spectra may be overwritten) -- working, not idling
+  auto help_until_mel_done = [&](unsigned b) {
+    for (unsigned spin = 0; load_acquire(&ctr->mel_done[b & 1]) < batch_goal(b);) {
+      if (try_store_task() || try_mel_task()) continue;
+      __nanosleep(20);
+      if (++spin > (1u << 22)) __trap();  // a protocol bug traps (error to the host) instead of hanging the GPU
+    }
+  };
+
+  // ---- main loop: one frame pair per ticket
+  unsigned ticket = 0;
+  if (lane == 0) ticket = atomicAdd(&ctr->fft_ticket, 1u);
+  ticket = __shfl_sync(kFullMask, ticket, 0);
+  float2 v[32];
+  {
+    const PairInfo first = describe_ticket(ticket);
+    if (first.interior) load_interior(p, first, lane, v);
+  }
+  while (ticket < n_tickets) {
+    const unsigned batch = ticket / kBatchPairs, position = ticket - batch * kBatchPairs;
+    float* slot = s_slots + position * kPosStride + (batch & 1) * kSlotFloats;
+    const PairInfo cur = describe_ticket(ticket);
+    const bool have_pair = cur.frame >= 0;
+    bool slot_free = batch < 2;
+    if (have_pair) {
+      if (!cur.interior) {
+        // edge frames: masked loads, staged through the pair's own slot sixteen rows at a time
+        if (!slot_free) help_until_mel_done(batch - 2);
+        slot_free = true;
+        float2* st2 = reinterpret_cast<float2*>(slot);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          load_edge(p.audio + (long long)cur.clip * p.audio_stride, p.n_samples, p.pad_mode, cur.fa_lo, cur.fb_lo,
+                    cur.lo_a, cur.hi_a, cur.lo_b, cur.hi_b, st2, 16 * half);
+          __syncwarp();
+#pragma unroll
+          for (int n1 = 0; n1 < 16; ++n1) v[bitrev5(16 * half + n1)] = st2[n1 * 32 + lane];
+          __syncwarp();
+        }
+      }
+      // periodic Hann window
 #pragma unroll
       for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = __fmul2_rn(v[bitrev5(n1)], bcast(s_hann[32 * n1 + lane]));
-      fft32(v);  // v[k1] = Y[k1] of column n2 = lane
-#pragma unroll
-      for (int k1 = 1; k1 < 32; ++k1) {
-        const float2 w = s_tw[k1 * 32 + lane];  // W_1024^(k1 * n2)
-        const float2 z = v[k1];
-        float2 r = __fmul2_rn(z, bcast(w.x));
-        v[k1] = __ffma2_rn(make_float2(-z.y, z.x), bcast(w.y), r);
-      }
-      // 32x32 transpose of complex values through the warp's padded tile
-#pragma unroll
-      for (int k1 = 0; k1 < 32; ++k1) xb2[k1 * kRowF2 + lane] = v[k1];
-      __syncwarp();
-#pragma unroll
-      for (int n2 = 0; n2 < 32; ++n2) v[bitrev5(n2)] = xb2[lane * kRowF2 + n2];
-      __syncwarp();
-      fft32(v);  // v[k2] = Z[lane + 32 * k2]
-
-      // separate the two real spectra: partner of k = lane + 32 r is 1024 - k = ((32-lane)&31) + 32 r'.
-      // Lanes 1..31: partner register r' = 31 - r; lane 0: r' = 32 - r, which is the value it fetched (from itself) one
-      // step earlier, and r = 0 is its own partner.  Four steps at a time: only 8 shuffle results are live at once.
-      const int src = (32 - lane) & 31;
-      float* pa = xb;
-      float* pb = xb + kSecondFrame;
-      float2 prev = v[0];
-#pragma unroll
-      for (int r0 = 0; r0 < 16; r0 += 4) {
-        float2 q[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          q[j].x = __shfl_sync(kFullMask, v[31 - r0 - j].x, src);
-          q[j].y = __shfl_sync(kFullMask, v[31 - r0 - j].y, src);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = r0 + j;
-          const float2 z = v[r];
-          const float2 c = lane == 0 ? prev : q[j];
-          prev = q[j];
-          // 2A = z + conj(c), 2iB = z - conj(c): (4|A|^2, 4|B|^2) = u*u + w*w, u = (z.x + c.x, z.x - c.x), w = (z.y - c.y, z.y + c.y)
-          const float2 u = __fadd2_rn(bcast(z.x), make_float2(c.x, -c.x));
-          const float2 w = __fadd2_rn(bcast(z.y), make_float2(-c.y, c.y));
-          const float2 pw = __ffma2_rn(w, w, __fmul2_rn(u, u));
-          pa[lane + 32 * r] = pw.x;
-          pb[lane + 32 * r] = pw.y;
-        }
-        asm volatile("" ::: "memory");  // keep the compiler from hoisting the next group's shuffles (register pressure)
-      }
-      if (lane == 0) {  // Nyquist bin 512 = register 16, self-paired: A = z.x, B = z.y (x4 like the others)
-        pa[512] = 4.0f * v[16].x * v[16].x;
-        pb[512] = 4.0f * v[16].y * v[16].y;
-      }
+      transform_first(v, s_tw, lane);
     }
-    // audio of the next iteration: in flight during the filterbank / store phases
-    nxt = locate_pair(p, it + gridDim.x < n_iters ? (it + gridDim.x) * kWarps + warp : total_pairs, total_pairs, ppc);
-    if (nxt.interior) load_interior(p, nxt, lane, v);
-    __syncthreads();
-
-    // ------------------------------------------------------------------ mel phase: lane = frame slot, warp = run of bins
+    // the slot still holds the spectra of batch - 2 until their filterbank is complete (and an arrival must not overtake
+    // that batch's arrivals in the counter either)
+    if (!slot_free) help_until_mel_done(batch - 2);
+    if (have_pair) transform_second(v, slot, lane);
+    __syncwarp();
+    if (lane == 0) add_release(&ctr->arrived[batch & 1]);
+    // next pair: its audio goes to registers now and is in flight while this warp serves filterbank / store tasks
+    if (lane == 0) ticket = atomicAdd(&ctr->fft_ticket, 1u);
+    ticket = __shfl_sync(kFullMask, ticket, 0);
     {
-      const float* spec = s_scratch + (lane >> 1) * kScratch + (lane & 1) * kSecondFrame;
-      if (kDefaultBank)
-        mel_phase_default(warp, spec, s_tlo + lane * kTileStride, s_thi + lane * kTileStride);
-      else
-        mel_phase_generic(s_runs[warp], s_runs[warp + 1], s_groups, s_binw, spec, s_tlo + lane * kTileStride,
-                          s_thi + lane * kTileStride);
+      const PairInfo nxt = describe_ticket(ticket);
+      if (nxt.interior) load_interior(p, nxt, lane, v);
     }
-    __syncthreads();
-
-    // ------------------------------------------------------------------ store phase: warp w owns slots 2w, 2w+1
-    if (cur.frame >= 0) {
-      const float* tlo = s_tlo + (2 * warp) * kTileStride;
-      const float* thi = s_thi + (2 * warp) * kTileStride;
-      float* dst = p.power + (long long)cur.clip * p.power_clip_stride + (long long)cur.frame * KOE_N_MELS;
-      // the 160 values of the two rows (row B follows row A in the clip's block), five per lane: j = lane + 32 q;
-      // j < 80 -> frame A filter j, else frame B filter j - 80, which sits kTileStride - 80 = 1 float further in the tile
-      float db[5];
-#pragma unroll
-      for (int qd = 0; qd < 5; ++qd) {
-        const int j = lane + 32 * qd;
-        const bool second = qd > 2 || (qd == 2 && lane >= KOE_N_MELS - 64);
-        const int t = j + (second ? kTileStride - KOE_N_MELS : 0);
-        db[qd] = db_from_power(tlo[t] + thi[t]);  // stored in dB: the consumer only subtracts its reference and clamps
-      }
-      float mx_a = fmaxf(db[0], db[1]), mx_b = fmaxf(db[3], db[4]);
-      if (lane < KOE_N_MELS - 64) mx_a = fmaxf(mx_a, db[2]); else mx_b = fmaxf(mx_b, db[2]);
-      dst[lane] = db[0];
-      dst[lane + 32] = db[1];
-      if (cur.has_b || lane < KOE_N_MELS - 64) dst[lane + 64] = db[2];
-      if (cur.has_b) {
-        dst[lane + 96] = db[3];
-        dst[lane + 128] = db[4];
-      }
-      if (p.frame_max != nullptr) {
-        const int ia = __reduce_max_sync(kFullMask, float_order(mx_a));
-        const int ib = __reduce_max_sync(kFullMask, float_order(mx_b));
-        float* fm = p.frame_max + (long long)cur.clip * p.fmax_clip_stride + cur.frame;
-        if (lane == 0) fm[0] = order_float(ia);
-        if (lane == 1 && cur.has_b) fm[1] = order_float(ib);
-      }
-    }
+#pragma unroll 1
+    for (int n = 0; n < 2; ++n)
+      if (!try_store_task()) break;
+#pragma unroll 1
+    for (int n = 0; n < 2; ++n)
+      if (!try_mel_task()) break;
+  }
+  // ---- no pairs left: drain the filterbank and store tasks
+  for (unsigned spin = 0; load_acquire(&ctr->store_ticket) < n_tickets;) {
+    if (try_store_task() || try_mel_task()) continue;
+    __nanosleep(20);
+    if (++spin > (1u << 22)) __trap();
   }
 }
 
-constexpr size_t kLogmelSmem = sizeof(float) * kFrameLen + sizeof(float2) * 1024 + sizeof(float2) * kMaxBins +
-                               sizeof(int4) * kMaxGroups + sizeof(int) * 32 +
-                               sizeof(float) * (2 * kSlots * kTileStride + kWarps * kScratch);
+constexpr size_t kLogmelSmem = kSmemCounterBytes + sizeof(float) * kFrameLen + sizeof(float2) * 1024 +
+                               sizeof(float2) * kMaxBins + sizeof(int4) * kMaxGroups + sizeof(int) * 32 +
+                               sizeof(float) * (4 * kTileFloats + kBatchPairs * kPosStride);
+static_assert(kLogmelSmem <= 232448, "shared memory budget of one SM");
 
 // ---- dB normalisation: ref = clip max, clamp, rescale; emits long-term and last-3 short-term features
 __global__ void logmel_normalise_kernel(const float* __restrict__ power, const float* __restrict__ frame_max,
@@ -534,7 +707,7 @@ struct koe_frontend {
   float* d_hann = nullptr;
   float2* d_tw = nullptr;
   float2* d_binw = nullptr;
-  int* d_tables = nullptr;  // groups[kMaxGroups] (int4) | runs[kWarps + 1 -> 32]
+  int* d_tables = nullptr;  // groups[kMaxGroups] (int4) | runs[kBatchPairs + 1 -> 32]
   int n_bins = 0, n_groups = 0;
   bool default_bank = false;  // structure == melbank_default.inc: the unrolled filterbank phase applies
   int num_sms = 0, occupancy = 0;
@@ -612,7 +785,7 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
   }
   fe->n_bins = (int)binw.size();
   fe->n_groups = n_groups;
-  // runs: contiguous group ranges, one per warp, balanced on bins + a per-group overhead (generic kernel only)
+  // runs: contiguous group ranges, one per filterbank task, balanced on bins + a per-group overhead (generic kernel only)
   {
     int* runs = tables.data() + 4 * kMaxGroups;
     auto cost = [&](int g) { return 3 + tables[4 * g + 2]; };
@@ -621,11 +794,11 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
     long long acc = 0;
     int r = 1;
     runs[0] = 0;
-    for (int g = 0; g < n_groups && r < kWarps; ++g) {
+    for (int g = 0; g < n_groups && r < kBatchPairs; ++g) {
       acc += cost(g);
-      if (acc * kWarps >= total * r) runs[r++] = g + 1;
+      if (acc * kBatchPairs >= total * r) runs[r++] = g + 1;
     }
-    for (; r <= kWarps; ++r) runs[r] = n_groups;
+    for (; r <= kBatchPairs; ++r) runs[r] = n_groups;
   }
   // the unrolled filterbank phase applies when the bank has the structure of melbank_default.inc and its weights
   // (computed above from the run-time arguments) equal the baked-in ones to within one float32 ulp
@@ -739,8 +912,9 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
   p.power_clip_stride = a->power_clip_stride;
   p.fmax_clip_stride = a->frame_max_clip_stride;
   const long long ppc = (a->n_frames + 1) / 2;
-  KOE_REQUIRE((long long)a->n_clips * ppc < (1ll << 31) - kWarps, "koe_logmel_power: more than 2^31 frame pairs in one call");
-  const long long n_blocks = ((long long)a->n_clips * ppc + kWarps - 1) / kWarps;
+  KOE_REQUIRE((long long)a->n_clips * ppc < (1ll << 31) - kBatchPairs * 65536ll,
+              "koe_logmel_power: more than 2^31 frame pairs in one call");
+  const long long n_blocks = ((long long)a->n_clips * ppc + kBatchPairs - 1) / kBatchPairs;
   const long long max_grid = (long long)fe->num_sms * fe->occupancy;
   const int grid = (int)std::min(n_blocks, max_grid);
   if (fe->default_bank)
