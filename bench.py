@@ -4,7 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp32|tf32|bf16]
 
 One step = SequentialDualStreamModel.forward over 512 synthetic 8.5 s clips (16 kHz, 30 fps, one output
-frame per clip) per GPU.  Prints ONE JSON line (see the task contract): `value` is the whole-job
+frame per clip) per GPU.  BASELINE.json quotes configs[1] in "fp32 and bf16": the line's value / dtype are the bf16
+tensor-core path (log-mel frontend in fp32 either way), `other_precision` carries the all-fp32 path of the same run.  Prints ONE JSON line (see the task contract): `value` is the whole-job
 audio-seconds per second with inputs resident in HBM; `e2e` is the same metric through the host-buffer API
 (pinned host audio -> H2D -> kernels -> D2H); `roofline` describes the dominant kernel; `cpu_baseline` is the
 oracle port of the reference's CPU forward timed on this box's host cores.
@@ -347,7 +348,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="koemorph_b200", choices=["koemorph_b200", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"],
+                    help="core kernel: bf16 = tcgen05 tensor path (bf16 operands, fp32 accumulation; default), fp32 = CUDA-core FMA; "
+                         "the other one is timed too and reported under other_precision")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--no-other-precision", action="store_true", help="skip the secondary (bf16 / fp32) leg")
