@@ -96,17 +96,19 @@ def run_reference(args):
         return
     clips_per_worker = 4
     pool, cores = _cpu_pool(clips_per_worker)
+    # one step = the GPU arm's step: ~512 clips, i.e. every worker forwards its 4 clips `reps` times
+    reps = max(1, -(-CLIPS_PER_GPU // (cores * clips_per_worker)))
     times = []
     with pool:
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            pool.map(_cpu_pass, [1] * cores, chunksize=1)
+            pool.map(_cpu_pass, [reps] * cores, chunksize=1)
             if i >= args.warmup:
                 times.append(time.perf_counter() - t0)
-    n = cores * clips_per_worker
+    n = cores * clips_per_worker * reps
     step = sum(times) / len(times)
     value = n * CLIP_SECONDS / step
-    sample = f"{n} clips of 8.5 s per step ({cores} processes x {clips_per_worker}) through " + _CPU_NOTE
+    sample = f"{n} clips of 8.5 s per step ({cores} processes x {clips_per_worker} clips x {reps} passes) through " + _CPU_NOTE
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
