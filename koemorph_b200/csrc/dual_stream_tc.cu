@@ -29,7 +29,7 @@ namespace tc {
 constexpr int kThreads = 320;   // warps 0-7 SIMT (two warpgroups), warp 8 TMA producer, warp 9 MMA issuer
 constexpr int kSimt = 256;
 constexpr int kStageBytes = 16384;
-constexpr int kRing = 4;
+constexpr int kRing = 6;             // 16 KiB stages; 6 so that the next window's mel rows prefetch behind the last weight stages
 constexpr int kTok = 80;
 constexpr int kKMel = 259;        // 30 fps only (mel_sequence_length 256 + 3)
 constexpr int kKMelPad = 272;     // multiple of 16
@@ -50,12 +50,18 @@ constexpr int kOffX = kOffConst + 1792 * 4;       // A1 (43520) / P tiles (40960
 constexpr int kOffE = kOffX + 10 * kA1Sbo;        // enc (40960) / Oflat
 constexpr int kOffVT = kOffE + 10 * kESbo;        // vT tiles (40960)
 constexpr int kOffRing = kOffVT + 2 * kPTile;
-constexpr int kSmemBytes = kOffRing + kRing * kStageBytes;   // 196352
+constexpr int kSmemBytes = kOffRing + kRing * kStageBytes;   // 229120
 static_assert(kOffX % 128 == 0 && kOffE % 128 == 0 && kOffVT % 128 == 0 && kOffRing % 128 == 0, "alignment");
 static_assert(kOffX + 16 * kA1Sbo <= kSmemBytes && kOffE + 16 * kESbo <= kSmemBytes, "operand over-read stays inside");
 
 // TMEM column map
 constexpr uint32_t kColD1 = 0, kColS = 256, kColVT = 0, kColO = 160, kColH = 0;
+
+// (dB - ref) clamped at -80 dB and rescaled to [0, 1], as normalise_db(., ., true) -- but the operand is rounded to bf16
+// next (2^-9 relative), so the exact fp32 division of the reference is replaced by one FFMA (<= 1 ulp of fp32 away)
+__device__ __forceinline__ float normalise_bf16(float db, float ref_db, bool) {
+  return fmaf(fmaxf(db - ref_db, -kTopDb), 1.0f / 80.0f, 1.0f);
+}
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              v[e] = 8 * c + e < rows ? normalise_db(raw[(8 * c + e) * kTok + j], ref_db, true) : 0.0f;
+              v[e] = 8 * c + e < rows ? normalise_bf16(raw[(8 * c + e) * kTok + j], ref_db, true) : 0.0f;
             *reinterpret_cast<uint4*>(smem + kOffX + (j >> 3) * kA1Sbo + (6 * s + c) * 128 + (j & 7) * 16) =
                 pack8_bf16(v);
           }
@@ -397,17 +403,17 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           for (int c = (Tl + 7) >> 3; c < 32; ++c) *reinterpret_cast<uint4*>(arow + c * 128) = make_uint4(0, 0, 0, 0);
           float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int e = 0; e < 3; ++e) v[e] = normalise_db(extra[e], ref_db, true);
+          for (int e = 0; e < 3; ++e) v[e] = normalise_bf16(extra[e], ref_db, true);
           *reinterpret_cast<uint4*>(arow + 32 * 128) = pack8_bf16(v);
           *reinterpret_cast<uint4*>(arow + 33 * 128) = make_uint4(0, 0, 0, 0);
           // edge frames inside the long-term range see zeros beyond the window edge: patch them in place
           if (p.n_edge > 0) {
-            *reinterpret_cast<__nv_bfloat16*>(arow) = __float2bfloat16_rn(normalise_db(extra[3], ref_db, true));
+            *reinterpret_cast<__nv_bfloat16*>(arow) = __float2bfloat16_rn(normalise_bf16(extra[3], ref_db, true));
             const int k = T - 1;
             if (k < Tl) {
               const float x = __ldg(p.power[2] + window_row(p, 2, b, wi, k) * kTok + j);
               *reinterpret_cast<__nv_bfloat16*>(arow + (k >> 3) * 128 + (k & 7) * 2) =
-                  __float2bfloat16_rn(normalise_db(x, ref_db, true));
+                  __float2bfloat16_rn(normalise_bf16(x, ref_db, true));
             }
           }
         }
@@ -460,10 +466,10 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
                 v[0][e] = r[e].x, v[1][e] = r[e].y, v[2][e] = r[e].z, v[3][e] = r[e].w;
               } else {
                 const bool real = 8 * c + e < kKMel;       // K tail 259..271 must be exact zeros
-                v[0][e] = real ? normalise_db(r[e].x, ref_db, true) : 0.0f;
-                v[1][e] = real ? normalise_db(r[e].y, ref_db, true) : 0.0f;
-                v[2][e] = real ? normalise_db(r[e].z, ref_db, true) : 0.0f;
-                v[3][e] = real ? normalise_db(r[e].w, ref_db, true) : 0.0f;
+                v[0][e] = real ? normalise_bf16(r[e].x, ref_db, true) : 0.0f;
+                v[1][e] = real ? normalise_bf16(r[e].y, ref_db, true) : 0.0f;
+                v[2][e] = real ? normalise_bf16(r[e].z, ref_db, true) : 0.0f;
+                v[3][e] = real ? normalise_bf16(r[e].w, ref_db, true) : 0.0f;
               }
             }
 #pragma unroll
@@ -561,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         float sum = 0.0f;
 #pragma unroll
         for (int i = 0; i < kTok; ++i) {
-          s[i] = expf(s[i] - m);
+          s[i] = __expf(s[i] - m);  // (the probabilities are rounded to bf16 next: MUFU.EX2 precision is ample)
           sum += s[i];
         }
         const float inv = lane < KOE_N_MOUTH ? 1.0f / sum : 0.0f;
