@@ -181,6 +181,8 @@ def run_gpu(args):
         raise RuntimeError("bench.py needs a CUDA device: koemorph_b200 has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from koemorph_b200.infer import bind_host_thread_to_gpu_node
+    numa_node = bind_host_thread_to_gpu_node(local) if world > 1 else None   # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
@@ -338,7 +340,8 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (CLIP_SAMPLES + 264) * 4,
                     "d2h_bytes_per_step": B * 52 * 4, "steps": e2e_steps,
-                    "api": "koemorph_b200.infer.HostPipeline (pinned host tensors, 64-clip chunks, 2 streams)"},
+                    "api": "koemorph_b200.infer.HostPipeline (pinned host tensors, 64-clip chunks, 2 streams)",
+                    "host_numa_node_rank0": numa_node},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "logmel_power_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,

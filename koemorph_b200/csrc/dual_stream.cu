@@ -48,6 +48,14 @@ __device__ __forceinline__ void gemm_acc(const float* __restrict__ As, int lda, 
     for (int i = 0; i < F4 / kCoreThreads; ++i) cp_async16(dst + tid + i * kCoreThreads, src + tid + i * kCoreThreads);
     cp_async_commit();
   };
+  // packed fp32x2 accumulators: acc2[i][j] = (acc[i][2j], acc[i][2j+1]); one FFMA2 (broadcast a, pair of b) does the work
+  // of two FFMAs in one issue slot -- same rounding per element, so the results are bit-identical to the scalar form
+  static_assert(TN % 2 == 0, "TN must be even");
+  float2 acc2[TM][TN / 2];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN / 2; ++j) acc2[i][j] = make_float2(acc[i][2 * j], acc[i][2 * j + 1]);
   issue(0);
   for (int c = 0; c < nchunks; ++c) {
     if (c + 1 < nchunks) {
@@ -62,7 +70,8 @@ __device__ __forceinline__ void gemm_acc(const float* __restrict__ As, int lda, 
     const int kmax = min(kKC, K - c * kKC);
 #pragma unroll 4
     for (int kk = 0; kk < kmax; ++kk) {
-      float a[TM], b[TN];
+      float a[TM];
+      float2 b[TN / 2];
       if constexpr (A_VEC2) {
 #pragma unroll
         for (int i = 0; i < TM / 2; ++i) {
@@ -75,14 +84,21 @@ __device__ __forceinline__ void gemm_acc(const float* __restrict__ As, int lda, 
         for (int i = 0; i < TM; ++i) a[i] = as[kk * lda + i];
       }
 #pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = bs[kk * NC + 32 * j];
+      for (int j = 0; j < TN / 2; ++j) b[j] = make_float2(bs[kk * NC + 64 * j], bs[kk * NC + 64 * j + 32]);
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN / 2; ++j) acc2[i][j] = __ffma2_rn(make_float2(a[i], a[i]), b[j], acc2[i][j]);
     }
     __syncthreads();
   }
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN / 2; ++j) {
+      acc[i][2 * j] = acc2[i][j].x;
+      acc[i][2 * j + 1] = acc2[i][j].y;
+    }
 }
 
 constexpr size_t kCoreSmemFloats = (size_t)kABlockRows * kTok      // A block

@@ -12,6 +12,40 @@ from typing import Optional
 import torch
 
 
+def bind_host_thread_to_gpu_node(device_index: int) -> Optional[int]:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that pinned buffers allocated afterwards
+    (first touch) and the copy threads live next to the PCIe root of that GPU -- with one process per GPU on a two-socket
+    box, cross-socket pinned memory otherwise caps the aggregate host->device bandwidth.  Returns the node, or None when
+    the topology is not exposed (containers without /sys access): nothing is changed then."""
+    import os
+    try:
+        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
+        if bdf is None:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs uses 4
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 class HostPipeline:
     def __init__(self, model, chunk_clips: int = 64):
         self.model = model
