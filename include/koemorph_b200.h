@@ -55,6 +55,28 @@ typedef struct koe_frontend koe_frontend_t; /* opaque: Hann window, FFT twiddles
 
 int koe_frontend_create(int device, int sample_rate, int n_fft, int n_mels, float fmin, float fmax,
                         koe_frontend_t** out);
+
+/*
+ * General form: also the torchaudio flavour of the reference's MelSpectrogramExtractor (src/features/stft.py:23-142:
+ * T.MelSpectrogram(n_fft=512, hop=sr/fps, mel_scale "htk", norm None, normalized=True, pad_mode "reflect") followed by
+ * log(mel + eps)).  n_fft is 1024 or 512 (a 512-point frame is transformed as the middle of a zero-extended 1024-point
+ * one); window_normalized divides the power by sum(window^2); log_mode selects what koe_logmel_power* store.
+ */
+#define KOE_MEL_SLANEY 0
+#define KOE_MEL_HTK 1
+#define KOE_MEL_NORM_NONE 0
+#define KOE_MEL_NORM_SLANEY 1
+#define KOE_LOG_DB 0     /* 10*log10(max(p, 1e-10)) */
+#define KOE_LOG_LN_EPS 1 /* ln(p + log_eps) */
+typedef struct {
+  int32_t device, sample_rate, n_fft, n_mels;
+  float fmin, fmax;
+  int32_t mel_scale, mel_norm;
+  int32_t window_normalized;
+  int32_t log_mode;
+  float log_eps;
+} koe_frontend_config;
+int koe_frontend_create_ex(const koe_frontend_config* cfg, koe_frontend_t** out);
 int koe_frontend_destroy(koe_frontend_t* fe);
 /* 1 when this frontend's filterbank has the structure of the path's default bank (sr 16000, 80 mels, 80..8000 Hz,
  * simplified_dual_stream_model.py:188-199) and runs the unrolled filterbank phase; 0: generic looped kernel */

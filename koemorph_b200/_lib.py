@@ -46,6 +46,13 @@ class LogmelArgs(C.Structure):
     ]
 
 
+class FrontendConfig(C.Structure):
+    """koe_frontend_config (include/koemorph_b200.h)."""
+    _fields_ = [("device", C.c_int32), ("sample_rate", C.c_int32), ("n_fft", C.c_int32), ("n_mels", C.c_int32),
+                ("fmin", C.c_float), ("fmax", C.c_float), ("mel_scale", C.c_int32), ("mel_norm", C.c_int32),
+                ("window_normalized", C.c_int32), ("log_mode", C.c_int32), ("log_eps", C.c_float)]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -56,6 +63,7 @@ _SIGNATURES = {
     "koe_reset_launch_count": (None, []),
     "koe_frontend_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                       C.POINTER(C.c_void_p)]),
+    "koe_frontend_create_ex": (C.c_int, [C.POINTER(FrontendConfig), C.POINTER(C.c_void_p)]),
     "koe_frontend_destroy": (C.c_int, [C.c_void_p]),
     "koe_frontend_filterbank_host": (C.c_int, [C.c_void_p, C.c_void_p]),
     "koe_frontend_uses_unrolled_bank": (C.c_int, [C.c_void_p]),

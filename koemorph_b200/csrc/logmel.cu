@@ -51,6 +51,8 @@ struct FrontendTables {
   const int4* groups;    // [n_groups] {first bin k, first entry of binw, number of bins, fl}: fl rises by one per group
   const int* runs;       // [kWarps + 1] group range of every warp in the filterbank phase
   int n_bins, n_groups;
+  int log_mode;          // 0: 10 log10(max(p, 1e-10)) (librosa power_to_db, first term); 1: ln(p + log_eps) (stft.py:124)
+  float log_eps;
 };
 
 struct LogmelParams {
@@ -196,6 +198,7 @@ __device__ __noinline__ void load_edge(const float* __restrict__ clip, int n_sam
   }
 }
 
+__device__ __forceinline__ float ln_from_power(float p, float eps) { return 0.69314718055994531f * __log2f(p + eps); }
 __device__ __forceinline__ float db_from_power(float p) {
   // 10 log10(max(p, amin)) = (10 log10 2) * log2(.): the argument is a normal number, MUFU.LG2 is within 2 ulp
   return 3.0102999566398120f * __log2f(fmaxf(p, kAmin));
@@ -306,7 +309,8 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   for (int i = tid; i < tab.n_bins; i += kThreads) s_binw[i] = tab.binw[i];
   for (int i = tid; i < tab.n_groups; i += kThreads) s_groups[i] = tab.groups[i];
   if (tid <= kWarps) s_runs[tid] = tab.runs[tid];
-  if (tid < kSlots) s_thi[tid * kTileStride] = 0.0f;  // filter 0 has no rising half from a lower interval
+  // cells that no group writes (filter 0's rising half; filters without a falling / rising group in sparse banks) stay 0
+  for (int i = tid; i < 2 * kSlots * kTileStride; i += kThreads) s_tlo[i] = 0.0f;
   __syncthreads();
 
   const unsigned ppc = (unsigned)(p.n_frames + 1) >> 1;  // frame pairs per clip
@@ -415,7 +419,9 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
         const int j = lane + 32 * qd;
         const bool second = qd > 2 || (qd == 2 && lane >= KOE_N_MELS - 64);
         const int t = j + (second ? kTileStride - KOE_N_MELS : 0);
-        db[qd] = db_from_power(tlo[t] + thi[t]);  // stored in dB: the consumer only subtracts its reference and clamps
+        const float pw = tlo[t] + thi[t];
+        // stored in dB (the consumer only subtracts its reference and clamps), or as ln(p + eps) for the torchaudio flavour
+        db[qd] = tab.log_mode == 0 ? db_from_power(pw) : ln_from_power(pw, tab.log_eps);
       }
       float mx_a = fmaxf(db[0], db[1]), mx_b = fmaxf(db[3], db[4]);
       if (lane < KOE_N_MELS - 64) mx_a = fmaxf(mx_a, db[2]); else mx_b = fmaxf(mx_b, db[2]);
@@ -487,6 +493,27 @@ __global__ void logmel_normalise_kernel(const float* __restrict__ power, const f
   }
 }
 
+// ---- host side: HTK filterbank without normalisation (torchaudio.functional.melscale_fbanks(mel_scale="htk", norm=None),
+// the bank of T.MelSpectrogram in the reference's src/features/stft.py:84-96), on the bins of an n_fft-point spectrum
+static std::vector<float> htk_filterbank(int sr, int n_fft, int n_mels, double fmin, double fmax) {
+  const int n_bins = 1 + n_fft / 2;
+  auto to_mel = [](double f) { return 2595.0 * std::log10(1.0 + f / 700.0); };
+  auto to_hz = [](double m) { return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0); };
+  std::vector<double> f_pts(n_mels + 2);
+  const double m0 = to_mel(fmin), m1 = to_mel(fmax);
+  for (int i = 0; i < n_mels + 2; ++i) f_pts[i] = to_hz(m0 + (m1 - m0) * i / (n_mels + 1));
+  std::vector<float> fb((size_t)n_mels * n_bins, 0.0f);
+  for (int m = 0; m < n_mels; ++m) {
+    const double d0 = f_pts[m + 1] - f_pts[m], d1 = f_pts[m + 2] - f_pts[m + 1];
+    for (int k = 0; k < n_bins; ++k) {
+      const double f = (double)(sr / 2) * k / (n_bins - 1);  // all_freqs = linspace(0, sr // 2, n_freqs)
+      const double down = (f - f_pts[m]) / d0, up = (f_pts[m + 2] - f) / d1;
+      fb[(size_t)m * n_bins + k] = (float)std::fmax(0.0, std::fmin(down, up));
+    }
+  }
+  return fb;
+}
+
 // ---- host side: Slaney filterbank (librosa.filters.mel restated, float64 then float32) -----------
 static double hz_to_mel(double f) {
   const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
@@ -531,6 +558,8 @@ using namespace koe;
 struct koe_frontend {
   int device = 0, sample_rate = 0, n_fft = 0, n_mels = 0;
   float fmin = 0, fmax = 0;
+  int log_mode = 0;
+  float log_eps = 0;
   float* d_hann = nullptr;
   float2* d_tw = nullptr;
   float2* d_binw = nullptr;
@@ -543,12 +572,36 @@ struct koe_frontend {
 
 extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n_mels, float fmin, float fmax,
                                    koe_frontend_t** out) {
-  KOE_REQUIRE(out != nullptr, "koe_frontend_create: out is NULL");
-  if (n_fft != KOE_N_FFT || n_mels != KOE_N_MELS)
-    return fail(KOE_E_UNSUPPORTED, "koe_frontend_create: only n_fft=1024, n_mels=80 are implemented (got %d, %d)",
+  koe_frontend_config c;
+  c.device = device;
+  c.sample_rate = sample_rate;
+  c.n_fft = n_fft;
+  c.n_mels = n_mels;
+  c.fmin = fmin;
+  c.fmax = fmax;
+  c.mel_scale = KOE_MEL_SLANEY;
+  c.mel_norm = KOE_MEL_NORM_SLANEY;
+  c.window_normalized = 0;
+  c.log_mode = KOE_LOG_DB;
+  c.log_eps = 0.0f;
+  return koe_frontend_create_ex(&c, out);
+}
+
+extern "C" int koe_frontend_create_ex(const koe_frontend_config* cfg, koe_frontend_t** out) {
+  KOE_REQUIRE(out != nullptr && cfg != nullptr, "koe_frontend_create: NULL argument");
+  const int device = cfg->device, sample_rate = cfg->sample_rate, n_fft = cfg->n_fft, n_mels = cfg->n_mels;
+  const float fmin = cfg->fmin, fmax = cfg->fmax;
+  if ((n_fft != KOE_N_FFT && n_fft != KOE_N_FFT / 2) || n_mels != KOE_N_MELS)
+    return fail(KOE_E_UNSUPPORTED, "koe_frontend_create: only n_fft=1024 or 512 and n_mels=80 are implemented (got %d, %d)",
                 n_fft, n_mels);
   KOE_REQUIRE(sample_rate > 0 && fmin >= 0 && fmax > fmin && fmax <= sample_rate / 2.0f,
               "koe_frontend_create: bad sample_rate/fmin/fmax");
+  KOE_REQUIRE((cfg->mel_scale == KOE_MEL_SLANEY && cfg->mel_norm == KOE_MEL_NORM_SLANEY) ||
+                  (cfg->mel_scale == KOE_MEL_HTK && cfg->mel_norm == KOE_MEL_NORM_NONE),
+              "koe_frontend_create: implemented banks are slaney scale + slaney norm (librosa) and htk scale + no norm "
+              "(torchaudio)");
+  KOE_REQUIRE((cfg->log_mode == KOE_LOG_DB) || (cfg->log_mode == KOE_LOG_LN_EPS && cfg->log_eps > 0),
+              "koe_frontend_create: bad log_mode / log_eps");
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
     return fail(KOE_E_NODEVICE, "koe_frontend_create: no CUDA device (this library has no CPU path)");
@@ -564,7 +617,31 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
   fe->n_mels = n_mels;
   fe->fmin = fmin;
   fe->fmax = fmax;
-  fe->fb_host = slaney_filterbank(sample_rate, n_fft, n_mels, fmin, fmax);
+  fe->log_mode = cfg->log_mode;
+  fe->log_eps = cfg->log_eps;
+  // The kernel always transforms 1024 samples.  A 512-point frame is the same frame zero-extended: its spectrum is the
+  // even bins of the 1024-point one (X_1024[2k] = X_512[k] up to a phase), so the window table holds the 512-point window
+  // in its middle and the bank puts its weights on the even bins.
+  const int sub = KOE_N_FFT / n_fft;  // 1 or 2
+  {
+    const std::vector<float> native = cfg->mel_scale == KOE_MEL_HTK
+                                          ? htk_filterbank(sample_rate, n_fft, n_mels, fmin, fmax)
+                                          : slaney_filterbank(sample_rate, n_fft, n_mels, fmin, fmax);
+    const int nb = 1 + n_fft / 2;
+    fe->fb_host.assign((size_t)n_mels * kBins, 0.0f);
+    for (int m = 0; m < n_mels; ++m)
+      for (int k = 0; k < nb; ++k) fe->fb_host[(size_t)m * kBins + sub * k] = native[(size_t)m * nb + k];
+  }
+  // periodic Hann of n_fft points, centred in the 1024-sample frame; torchaudio's normalized=True ("window") divides the
+  // STFT by sqrt(sum w^2), i.e. the power by sum w^2: folded into the sparse weights below
+  std::vector<float> hann(kFrameLen, 0.0f);
+  double wsum2 = 0.0;
+  for (int n = 0; n < n_fft; ++n) {
+    const double w = 0.5 - 0.5 * std::cos(2.0 * M_PI * n / n_fft);
+    hann[(kFrameLen - n_fft) / 2 + n] = (float)w;
+    wsum2 += (double)(float)w * (double)(float)w;
+  }
+  const float wscale = cfg->window_normalized ? (float)(0.25 / wsum2) : 0.25f;  // 0.25: the kernel leaves 4 |X|^2
 
   // bin-major sparse filterbank: every weighted bin feeds one filter or two adjacent ones (fl, fl + 1); consecutive bins
   // with the same fl form a group (the interval between two filter centres), and fl rises by one from group to group
@@ -589,10 +666,15 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
         }
       if (count == 0) continue;
       if (count > 2 || last - first > 1) return unsupported("more than two / non-adjacent filters", k);
+      // bins without weight inside the support (the odd bins of a 512-point bank) ride along in the current group
+      for (int z = prev_k + 1; prev_k >= 0 && z < k; ++z) {
+        if ((int)binw.size() >= kMaxBins) return unsupported("too many weighted bins", z);
+        ++tables[4 * (n_groups - 1) + 2];
+        binw.push_back(make_float2(0.0f, 0.0f));
+      }
       if ((int)binw.size() >= kMaxBins) return unsupported("too many weighted bins", k);
-      if (prev_k >= 0 && k != prev_k + 1) return unsupported("gap in the weighted bins", k);
       if (first != prev_fl) {
-        if (first != prev_fl + 1) return unsupported("filters skipped", k);
+        if (first < prev_fl) return unsupported("filters out of order", k);
         if (n_groups >= kMaxGroups) return unsupported("too many groups", k);
         tables[4 * n_groups + 0] = k;
         tables[4 * n_groups + 1] = (int)binw.size();
@@ -602,13 +684,12 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
       }
       ++tables[4 * (n_groups - 1) + 2];
       bin_group[k] = (unsigned char)first;
-      // 0.25: the kernel leaves 4 |X|^2 in the spectrum (exact power-of-two scaling)
-      binw.push_back(make_float2(0.25f * fe->fb_host[(size_t)first * kBins + k],
-                                 count == 2 ? 0.25f * fe->fb_host[(size_t)last * kBins + k] : 0.0f));
+      binw.push_back(make_float2(wscale * fe->fb_host[(size_t)first * kBins + k],
+                                 count == 2 ? wscale * fe->fb_host[(size_t)last * kBins + k] : 0.0f));
       prev_k = k;
       prev_fl = first;
     }
-    if (n_groups != n_mels) return unsupported("a filter without a falling half", kBins);
+    if (n_groups == 0) return unsupported("empty bank", 0);
   }
   fe->n_bins = (int)binw.size();
   fe->n_groups = n_groups;
@@ -629,15 +710,13 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
   }
   // the unrolled filterbank phase applies when the bank has the structure of melbank_default.inc and its weights
   // (computed above from the run-time arguments) equal the baked-in ones to within one float32 ulp
-  fe->default_bank = fe->n_bins == kDefNumBins && tables[0] == kDefFirstBin &&
+  fe->default_bank = sub == 1 && !cfg->window_normalized && fe->n_bins == kDefNumBins && tables[0] == kDefFirstBin &&
                      std::equal(bin_group.begin(), bin_group.end(), kDefBinGroup);
   for (int i = 0; fe->default_bank && i < kDefNumBins; ++i) {
     const float got[2] = {binw[i].x, binw[i].y}, want[2] = {kDefBinW[2 * i], kDefBinW[2 * i + 1]};
     for (int h = 0; h < 2; ++h)
       if (std::fabs(got[h] - want[h]) > 1.2e-7f * std::fabs(want[h])) fe->default_bank = false;
   }
-  std::vector<float> hann(kFrameLen);
-  for (int n = 0; n < kFrameLen; ++n) hann[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / kFrameLen));
   std::vector<float2> tw(1024);
   for (int k1 = 0; k1 < 32; ++k1)
     for (int n2 = 0; n2 < 32; ++n2) {
@@ -721,6 +800,8 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
   tab.runs = fe->d_tables + 4 * kMaxGroups;
   tab.n_bins = fe->n_bins;
   tab.n_groups = fe->n_groups;
+  tab.log_mode = fe->log_mode;
+  tab.log_eps = fe->log_eps;
   LogmelParams p;
   p.audio = a->audio;
   p.audio_stride = a->audio_stride;

@@ -24,25 +24,35 @@ class LogMelFrontend:
     _cache: Dict[Tuple, "LogMelFrontend"] = {}
 
     def __init__(self, device, sample_rate: int = 16000, n_fft: int = N_FFT, n_mels: int = N_MELS,
-                 f_min: float = 80.0, f_max: float = 8000.0):
+                 f_min: float = 80.0, f_max: float = 8000.0, mel_scale: str = "slaney", window_normalized: bool = False,
+                 log_mode: str = "db", log_eps: float = 0.0):
+        """``mel_scale`` "slaney" (librosa: Slaney scale, slaney norm) or "htk" (torchaudio default: HTK scale, no norm);
+        ``log_mode`` "db" = 10 log10(max(p, 1e-10)) or "ln" = ln(p + log_eps); ``n_fft`` 1024 or 512."""
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError(f"LogMelFrontend needs a CUDA device, got {device}; there is no CPU path")
+        if mel_scale not in ("slaney", "htk") or log_mode not in ("db", "ln"):
+            raise ValueError("mel_scale must be 'slaney' or 'htk', log_mode 'db' or 'ln'")
         self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
         self.sample_rate, self.n_fft, self.n_mels, self.f_min, self.f_max = sample_rate, n_fft, n_mels, f_min, f_max
         self._lib = _lib.load()
+        cfg = _lib.FrontendConfig(self.device.index, sample_rate, n_fft, n_mels, float(f_min), float(f_max),
+                                  1 if mel_scale == "htk" else 0, 0 if mel_scale == "htk" else 1,
+                                  int(bool(window_normalized)), 1 if log_mode == "ln" else 0, float(log_eps))
         h = C.c_void_p()
-        _lib.check(self._lib.koe_frontend_create(self.device.index, sample_rate, n_fft, n_mels, float(f_min),
-                                                 float(f_max), C.byref(h)), "koe_frontend_create")
+        _lib.check(self._lib.koe_frontend_create_ex(C.byref(cfg), C.byref(h)), "koe_frontend_create_ex")
         self._h = h
 
     @classmethod
-    def get(cls, device, sample_rate=16000, n_fft=N_FFT, n_mels=N_MELS, f_min=80.0, f_max=8000.0):
+    def get(cls, device, sample_rate=16000, n_fft=N_FFT, n_mels=N_MELS, f_min=80.0, f_max=8000.0, mel_scale="slaney",
+            window_normalized=False, log_mode="db", log_eps=0.0):
         device = torch.device(device)
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        key = (idx, sample_rate, n_fft, n_mels, float(f_min), float(f_max))
+        key = (idx, sample_rate, n_fft, n_mels, float(f_min), float(f_max), mel_scale, bool(window_normalized), log_mode,
+               float(log_eps))
         if key not in cls._cache:
-            cls._cache[key] = cls(torch.device("cuda", idx), sample_rate, n_fft, n_mels, f_min, f_max)
+            cls._cache[key] = cls(torch.device("cuda", idx), sample_rate, n_fft, n_mels, f_min, f_max, mel_scale,
+                                  window_normalized, log_mode, log_eps)
         return cls._cache[key]
 
     def __del__(self):
@@ -59,9 +69,11 @@ class LogMelFrontend:
         return bool(self._lib.koe_frontend_uses_unrolled_bank(self._h))
 
     def filterbank(self) -> np.ndarray:
-        fb = np.empty((self.n_mels, 1 + self.n_fft // 2), np.float32)
+        """Dense (n_mels, 1 + n_fft // 2) float32 filterbank (the library keeps it on the bins of its 1024-point
+        transform; a 512-point bank sits on the even bins)."""
+        fb = np.empty((self.n_mels, 1 + N_FFT // 2), np.float32)
         _lib.check(self._lib.koe_frontend_filterbank_host(self._h, fb.ctypes.data_as(C.c_void_p)))
-        return fb
+        return np.ascontiguousarray(fb[:, ::N_FFT // self.n_fft])
 
     def power(self, audio: torch.Tensor, hop: int, n_frames: int, frame_offset: int = 0, frame_step: int = 1,
               lo_rel: Optional[int] = None, hi_rel: Optional[int] = None,

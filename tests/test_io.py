@@ -62,3 +62,22 @@ def test_streamer_udp_and_file(tmp_path):
         kio.BlendshapeStreamer("osc")
     with pytest.raises(ValueError):
         kio.BlendshapeStreamer("udp").send([0.0] * 3, 0.0)
+
+
+def test_stft_golden_fixture_is_complete():
+    """tests/golden/stft_reference.npz (outputs of the unmodified reference src/features/stft.py) covers every case of
+    tests/golden/make_golden_stft.py with the frame count the reference contract gives: int(L / sr * fps)."""
+    import os
+    import sys
+    import numpy as np
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    from make_golden_stft import CASES, stft_inputs
+    data = np.load(os.path.join(here, "stft_reference.npz"))
+    for name, (seed, B, L, kind, kw) in CASES.items():
+        fps = kw.get("target_fps", 30.0)
+        assert data[f"{name}/log_mel"].shape == (B, int(L / 16000 * fps), 80)
+        assert data[f"{name}/mel_scale"].shape == (kw.get("n_fft", 512) // 2 + 1, 80)
+        assert np.isfinite(data[f"{name}/log_mel"]).all()
+    x = stft_inputs(11, 2, 16000, "noise")
+    assert x.shape == (2, 16000) and torch.equal(x, stft_inputs(11, 2, 16000, "noise"))
