@@ -31,15 +31,22 @@ constexpr int kSimt = 256;
 constexpr int kStageBytes = 16384;
 constexpr int kRing = 6;             // 16 KiB stages; 6 so that the next window's mel rows prefetch behind the last weight stages
 constexpr int kTok = 80;
-constexpr int kKMel = 259;        // 30 fps only (mel_sequence_length 256 + 3)
-constexpr int kKMelPad = 272;     // multiple of 16
-constexpr int kA1Chunks = kKMelPad / 8;           // 34 16-byte K chunks per row
-constexpr int kA1Sbo = kA1Chunks * 128;           // 4352
+// Window geometry: K of the first GEMM = mel_sequence_length + 3 = 259 (30 fps) or 515 (60 fps)
+template <int KMEL>
+struct Geo {
+  static constexpr int kKMel = KMEL;
+  static constexpr int kKMelPad = (KMEL + 15) / 16 * 16;        // 272 / 528
+  static constexpr int kA1Chunks = kKMelPad / 8;                // 34 / 66 16-byte K chunks per row
+  static constexpr int kA1Sbo = kA1Chunks * 128;                // 4352 / 8448
+  static constexpr int kLongChunks = (KMEL - 3) / 8;            // 32 / 64 chunks of long-term frames, then the short-term chunk
+  static constexpr int kStagesG1 = (kKMelPad + 31) / 32;        // 9 / 17 weight stages of [256 x 32]; the last is half full
+  static constexpr int kStagesPerWindow = kStagesG1 + 20;       // + 5 x 4 stages of [128 x 64]
+};
+constexpr int kA1Sbo30 = Geo<259>::kA1Sbo;
 constexpr int kESbo = 32 * 128;                   // enc / Oflat: K = 256 -> 32 chunks
 constexpr int kPSbo = 10 * 128;                   // P / vT tiles: K = 80 -> 10 chunks
 constexpr int kPTile = 16 * kPSbo;                // 20480
-constexpr int kStagesG1 = 9, kStagesTile = 4;
-constexpr int kStagesPerWindow = kStagesG1 + 5 * kStagesTile;  // 29 weight stages
+constexpr int kStagesTile = 4;
 constexpr int kMelRows = 48;                      // mel rows (frames) per ring stage: 48 * 320 B = 15360 B, 6 K-chunks
 constexpr int kMelStageBytes = kMelRows * kTok * 4;
 
@@ -47,12 +54,14 @@ constexpr int kMelStageBytes = kMelRows * kTok * 4;
 constexpr int kOffBar = 0;                        // mbarriers + tmem base
 constexpr int kOffConst = 256;                    // bc, ln_g, ln_b, bv (256 each), ba, w2 (128 each), LN partials (512)
 constexpr int kOffX = kOffConst + 1792 * 4;       // A1 (43520) / P tiles (40960)
-constexpr int kOffE = kOffX + 10 * kA1Sbo;        // enc (40960) / Oflat
+constexpr int kOffE = kOffX + 10 * kA1Sbo30;      // enc (40960) / Oflat; at 60 fps the A1 operand (84480 B) spans X and E, which is
+                                                  // free until the LayerNorm epilogue writes enc after the first GEMM
 constexpr int kOffVT = kOffE + 10 * kESbo;        // vT tiles (40960)
 constexpr int kOffRing = kOffVT + 2 * kPTile;
 constexpr int kSmemBytes = kOffRing + kRing * kStageBytes;   // 229120
 static_assert(kOffX % 128 == 0 && kOffE % 128 == 0 && kOffVT % 128 == 0 && kOffRing % 128 == 0, "alignment");
-static_assert(kOffX + 16 * kA1Sbo <= kSmemBytes && kOffE + 16 * kESbo <= kSmemBytes, "operand over-read stays inside");
+static_assert(kOffX + 16 * Geo<515>::kA1Sbo <= kSmemBytes && kOffE + 16 * kESbo <= kSmemBytes, "operand over-read stays inside");
+static_assert(kOffX + 10 * Geo<515>::kA1Sbo <= kOffVT, "the 60 fps A1 operand ends where the vT tiles begin");
 
 // TMEM column map
 constexpr uint32_t kColD1 = 0, kColS = 256, kColVT = 0, kColO = 160, kColH = 0;
@@ -165,7 +174,11 @@ __device__ __forceinline__ void stamp(long long* dbg, int slot) {
 
 __device__ __forceinline__ void simt_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+template <int KMEL>
 __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams p) {
+  using G = Geo<KMEL>;
+  constexpr int kKMel = G::kKMel, kA1Chunks = G::kA1Chunks, kA1Sbo = G::kA1Sbo, kLongChunks = G::kLongChunks;
+  constexpr int kStagesG1 = G::kStagesG1, kStagesPerWindow = G::kStagesPerWindow;
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -400,18 +413,21 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           const int j = tid;
           unsigned char* arow = smem + kOffX + (j >> 3) * kA1Sbo + (j & 7) * 16;
           // K chunks past the long-term frames: zeros up to frame 255, then [short-term x3, 0 x5], then zeros
-          for (int c = (Tl + 7) >> 3; c < 32; ++c) *reinterpret_cast<uint4*>(arow + c * 128) = make_uint4(0, 0, 0, 0);
+          for (int c = (Tl + 7) >> 3; c < kLongChunks; ++c) *reinterpret_cast<uint4*>(arow + c * 128) = make_uint4(0, 0, 0, 0);
           float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int e = 0; e < 3; ++e) v[e] = normalise_bf16(extra[e], ref_db, true);
-          *reinterpret_cast<uint4*>(arow + 32 * 128) = pack8_bf16(v);
-          *reinterpret_cast<uint4*>(arow + 33 * 128) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(arow + kLongChunks * 128) = pack8_bf16(v);
+          *reinterpret_cast<uint4*>(arow + (kLongChunks + 1) * 128) = make_uint4(0, 0, 0, 0);
           // edge frames inside the long-term range see zeros beyond the window edge: patch them in place
-          if (p.n_edge > 0) {
-            *reinterpret_cast<__nv_bfloat16*>(arow) = __float2bfloat16_rn(normalise_bf16(extra[3], ref_db, true));
-            const int k = T - 1;
+          // (frame m and frame T-1-m for m < n_edge: one per side at 30 fps, two at 60 fps)
+          for (int m = 0; m < p.n_edge; ++m) {
+            const float lo = m == 0 ? extra[3] : __ldg(p.power[1 + 2 * m] + window_row(p, 1 + 2 * m, b, wi, m) * kTok + j);
+            *reinterpret_cast<__nv_bfloat16*>(arow + (m >> 3) * 128 + (m & 7) * 2) =
+                __float2bfloat16_rn(normalise_bf16(lo, ref_db, true));
+            const int k = T - 1 - m;
             if (k < Tl) {
-              const float x = __ldg(p.power[2] + window_row(p, 2, b, wi, k) * kTok + j);
+              const float x = __ldg(p.power[2 + 2 * m] + window_row(p, 2 + 2 * m, b, wi, k) * kTok + j);
               *reinterpret_cast<__nv_bfloat16*>(arow + (k >> 3) * 128 + (k & 7) * 2) =
                   __float2bfloat16_rn(normalise_bf16(x, ref_db, true));
             }
@@ -674,17 +690,20 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
 int launch_dual_stream_tc(const CoreParams& p, int precision, cudaStream_t stream) {
   if (precision != 2)
     return fail(KOE_E_UNSUPPORTED, "tensor-core path: only precision 2 (bf16 operands) is built; tf32 is not");
-  if (p.w.tc_bf16 == nullptr || p.w.tc_stages != tc::kStagesPerWindow)
+  if (p.w.k_mel != 259 && p.w.k_mel != 515)
+    return fail(KOE_E_UNSUPPORTED, "tensor-core path is built for k_mel = 259 (30 fps) and 515 (60 fps); got %d", p.w.k_mel);
+  const int need_stages = p.w.k_mel == 259 ? tc::Geo<259>::kStagesPerWindow : tc::Geo<515>::kStagesPerWindow;
+  if (p.w.tc_bf16 == nullptr || p.w.tc_stages != need_stages)
     return fail(KOE_E_INVALID, "tensor-core path: koe_core_weights.tc_bf16 is missing (%d stages, need %d)",
-                p.w.tc_stages, tc::kStagesPerWindow);
-  if (p.w.k_mel != tc::kKMel)
-    return fail(KOE_E_UNSUPPORTED, "tensor-core path is built for k_mel = 259 (30 fps); got %d", p.w.k_mel);
+                p.w.tc_stages, need_stages);
   static int num_sms[64] = {0};
   int dev = 0;
   KOE_CUDA(cudaGetDevice(&dev));
   KOE_REQUIRE(dev >= 0 && dev < 64, "device index too large");
   if (num_sms[dev] == 0) {
-    KOE_CUDA(cudaFuncSetAttribute(tc::dual_stream_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    KOE_CUDA(cudaFuncSetAttribute(tc::dual_stream_tc_kernel<259>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tc::kSmemBytes));
+    KOE_CUDA(cudaFuncSetAttribute(tc::dual_stream_tc_kernel<515>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   tc::kSmemBytes));
     int n = 0;
     KOE_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
@@ -694,7 +713,10 @@ int launch_dual_stream_tc(const CoreParams& p, int precision, cudaStream_t strea
     KOE_CUDA(cudaMemsetAsync(p.attn_out, 0, (size_t)p.n_clips * p.n_out * KOE_N_MOUTH * tc::kTok * sizeof(float),
                              stream));
   const int grid = std::min(p.n_clips * p.n_out, num_sms[dev]);
-  tc::dual_stream_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(p);
+  if (p.w.k_mel == 259)
+    tc::dual_stream_tc_kernel<259><<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(p);
+  else
+    tc::dual_stream_tc_kernel<515><<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(p);
   count_launch();
   KOE_CUDA(cudaGetLastError());
   return KOE_OK;

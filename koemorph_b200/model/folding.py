@@ -131,15 +131,16 @@ def fold(sd: Dict[str, torch.Tensor], num_heads: int, temperature: float, device
         "eln_g": f32(g("emotion_norm.weight")), "eln_b": f32(g("emotion_norm.bias")),
         "we2_t": f32(we2.T), "be2": f32(be2),
     }
-    if k_mel == 259:
-        # tcgen05 path: stage images in consumption order -- Wc (9 x [256 x 32]), Qk tiles 0/1, Wv tiles 0/1,
-        # Wa (each 4 x [128 x 64]); Qk rows are re-indexed to 32*h + q (queries 28..31 of each head are zero rows)
+    if k_mel in (259, 515):
+        # tcgen05 path: stage images in consumption order -- Wc (9 x [256 x 32] at 30 fps, 17 at 60 fps), Qk tiles 0/1,
+        # Wv tiles 0/1, Wa (each 4 x [128 x 64]); Qk rows are re-indexed to 32*h + q (queries 28..31 of each head are zero rows)
         qk_pad = torch.zeros(256, d, dtype=dd, device=device)
         for h in range(num_heads):
             qk_pad[32 * h:32 * h + nq] = qk[h * nq:(h + 1) * nq]
-        stages = _tile_kmajor(wc, 256, 32, 288) + _tile_kmajor(qk_pad, 128, 64, 256) + \
+        n_g1 = (_ceil_to(k_mel, 16) + 31) // 32
+        stages = _tile_kmajor(wc, 256, 32, 32 * n_g1) + _tile_kmajor(qk_pad, 128, 64, 256) + \
             _tile_kmajor(wv, 128, 64, 256) + _tile_kmajor(wa, 128, 64, 256)
         tensors["tc_bf16"] = torch.cat(stages).to(torch.bfloat16).contiguous()
-        assert tensors["tc_bf16"].numel() * 2 == 29 * TC_STAGE_BYTES
+        assert tensors["tc_bf16"].numel() * 2 == (n_g1 + 20) * TC_STAGE_BYTES
     b2 = float(sd["blendshape_decoder.3.bias"].detach().reshape(-1)[0])
     return CoreWeights(tensors, k_mel, emo_in, b2, eps)

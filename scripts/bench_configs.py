@@ -5,7 +5,7 @@
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_configs.py --configs c5
 
 Prints one JSON line per config (rank 0).  Synthetic data, random-init weights (oracle.make_weights, test infra).
-  c3  60 fps mode (hop 266, 512-frame window, K = 515): 512 clips x 8.5 s, one output frame per clip, fp32 core
+  c3  60 fps mode (hop 266, 512-frame window, K = 515): 512 clips x 8.5 s, one output frame per clip, both cores
   c4  streaming: S concurrent streams, rings pre-filled with 8.5 s, then 300 steps of one hop per stream; per-step
       latency measured on the host (submit -> outputs complete), p50 / p99
   c5  corpus sweep: N clips sharded by clip over the ranks, 512-clip chunks from a small pool of device buffers,
@@ -53,13 +53,16 @@ def timed(fn, steps, warmup=3):
 
 
 def c3(dev, args):
-    m = make_model(60, dev, "fp32")
+    m = make_model(60, dev, args.precision)
     B = 512
     audio = 0.1 * torch.randn(B, 136000, device=dev)
     eg = torch.randn(B, 264, device=dev)
     ms = timed(lambda: m(audio, egemaps=eg), 20)
-    return {"config": "c3: 60 fps (hop 266, 512-frame window, K=515), 512 x 8.5 s clips, 1 frame/clip", "dtype": "f32",
-            "ms_per_step": ms, "value": B * 8.5 / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": 1}
+    m.precision = "fp32" if args.precision == "bf16" else "bf16"
+    ms_other = timed(lambda: m(audio, egemaps=eg), 20)
+    return {"config": "c3: 60 fps (hop 266, 512-frame window, K=515), 512 x 8.5 s clips, 1 frame/clip",
+            "dtype": args.precision, "ms_per_step": ms, "value": B * 8.5 / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": 1,
+            "other_precision": {"precision": m.precision, "ms_per_step": ms_other, "value": B * 8.5 / (ms_other * 1e-3)}}
 
 
 def c4(dev, args):

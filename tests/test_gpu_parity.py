@@ -257,7 +257,7 @@ BF16_OUT_ATOL, BF16_SIG_ATOL, BF16_ATTN_ATOL = 1e-4, 2e-3, 2e-3
 
 
 @pytest.mark.parametrize("name", ["single_noise_init", "single_speech_stress", "single_burst_stress",
-                                  "single_silence_init", "single_short_clip", "single_long_clip"])
+                                  "single_silence_init", "single_short_clip", "single_long_clip", "single_60fps"])
 def test_bf16_tensor_path_single(K, golden, name):
     cases, data = golden
     spec = cases[name]
@@ -273,7 +273,7 @@ def test_bf16_tensor_path_single(K, golden, name):
     assert float((rows - 1).abs().max()) < 1e-2
 
 
-@pytest.mark.parametrize("name", ["seq_clip_T1", "seq_13_frames", "seq_20s", "seq_stride3", "seq_burst_edge"])
+@pytest.mark.parametrize("name", ["seq_clip_T1", "seq_13_frames", "seq_20s", "seq_stride3", "seq_burst_edge", "seq_60fps"])
 def test_bf16_tensor_path_sequence(K, golden, name):
     cases, data = golden
     spec = cases[name]
@@ -301,8 +301,10 @@ def test_bf16_tensor_path_full_batch_consistency(K):
     assert torch.equal(out_p, out[perm])
 
 
-def test_bf16_60fps_is_refused_not_faked(K):
-    m = K.SequentialDualStreamModel(target_fps=60, mel_sequence_length=512).cuda()
+def test_bf16_unsupported_geometry_is_refused_not_faked(K):
+    """The tensor path is built for K = 259 (30 fps) and 515 (60 fps); any other window length has no pre-tiled bf16
+    weights and must raise instead of silently running something else."""
+    m = K.SequentialDualStreamModel(target_fps=30, mel_sequence_length=128).cuda()
     m.precision = "bf16"
     with pytest.raises(RuntimeError, match="tc_bf16 is missing|30 fps"):
         m(torch.zeros(1, 136000, device="cuda"), egemaps=torch.zeros(1, 264, device="cuda"))
