@@ -497,6 +497,18 @@ __global__ void __launch_bounds__(256) emotion_stream_kernel(koe_core_weights W,
 constexpr int kEmaTile = 32;
 constexpr int kEmaStride = KOE_N_BLENDSHAPES + 1;
 
+// one frame per clip (the streaming step): y = alpha x + (1 - alpha) state, or x itself for the first frame -- the same
+// roundings as the scan kernel below for n_out == 1
+__global__ void __launch_bounds__(256) ema_step_kernel(float* __restrict__ frames, int n, float alpha,
+                                                       float* __restrict__ state, int has_state) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float x = frames[i];
+  const float y = (has_state && state != nullptr) ? fmaf(1.0f - alpha, state[i], alpha * x) : x;
+  frames[i] = y;
+  if (state != nullptr) state[i] = y;
+}
+
 __global__ void __launch_bounds__(256) ema_scan_kernel(float* __restrict__ frames, int n_out, float alpha,
                                                        float* __restrict__ state, int has_state) {
   __shared__ float s_t[kEmaTile * kEmaStride];
@@ -734,7 +746,11 @@ extern "C" int koe_ema_scan(float* frames, int n_clips, int n_out, float alpha, 
   KOE_REQUIRE(alpha >= 0.0f && alpha <= 1.0f, "koe_ema_scan: alpha must be in [0, 1]");
   KOE_REQUIRE(!has_state || state != nullptr, "koe_ema_scan: has_state set but state is NULL");
   if (n_clips == 0 || n_out == 0) return KOE_OK;
-  ema_scan_kernel<<<n_clips, 256, 0, (cudaStream_t)stream>>>(frames, n_out, alpha, state, has_state);
+  if (n_out == 1)
+    ema_step_kernel<<<(n_clips * KOE_N_BLENDSHAPES + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        frames, n_clips * KOE_N_BLENDSHAPES, alpha, state, has_state);
+  else
+    ema_scan_kernel<<<n_clips, 256, 0, (cudaStream_t)stream>>>(frames, n_out, alpha, state, has_state);
   count_launch();
   KOE_CUDA(cudaGetLastError());
   return KOE_OK;

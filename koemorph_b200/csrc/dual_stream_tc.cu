@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
 
   const int n_items = p.n_clips * p.n_out;
   const int T = p.frames_per_window;
-  // plain linear layout (not prenormalised features, not the streaming rings): mel rows arrive by TMA
-  const bool tma_mel = p.mel_long == nullptr && p.ring_frames == 0;
+  // mel power rows (linear buffer or per-stream ring; not prenormalised features) arrive by TMA
+  const bool tma_mel = p.mel_long == nullptr;
   const int Tl = min(T, p.mel_seq);                              // long-term frames actually present
   const int n_mel_stages = tma_mel ? (Tl + kMelRows - 1) / kMelRows : 0;
 
@@ -246,14 +246,24 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           // the window's plain mel rows [0, Tl) are contiguous in HBM: stream them through the same ring, ahead of the
           // weights, so that by the time the SIMT warps start a window its rows are already in shared memory
           const int b = item / p.n_out, wi = item % p.n_out;
-          const unsigned char* rows =
-              reinterpret_cast<const unsigned char*>(p.power[0] + window_row(p, 0, b, wi, 0) * kTok);
+          // linear buffer: rows [0, Tl) of the window are contiguous; ring: row k is slot (ring_base + k) % ring_frames of
+          // the stream's ring, i.e. at most two contiguous runs per stage
+          const float* base = p.ring_frames > 0 ? p.power[0] + (size_t)b * p.ring_frames * kTok
+                                                : p.power[0] + window_row(p, 0, b, wi, 0) * kTok;
           for (int s = 0; s < n_mel_stages; ++s) {
-            const uint32_t bytes = (uint32_t)min(kMelRows, Tl - kMelRows * s) * kTok * 4;
+            const int n = min(kMelRows, Tl - kMelRows * s);
+            const uint32_t bytes = (uint32_t)n * kTok * 4;
+            const uint32_t dst = sbase + kOffRing + slot * kStageBytes;
             mbar_wait(bar_empty + 8 * slot, phase ^ 1);
             mbar_expect_tx(bar_full + 8 * slot, bytes);
-            bulk_g2s(sbase + kOffRing + slot * kStageBytes, rows + (size_t)s * kMelStageBytes, bytes,
-                     bar_full + 8 * slot);
+            if (p.ring_frames > 0) {
+              const int r0 = (p.ring_base + kMelRows * s) % p.ring_frames;
+              const int n1 = min(n, p.ring_frames - r0);
+              bulk_g2s(dst, base + (size_t)r0 * kTok, (uint32_t)n1 * kTok * 4, bar_full + 8 * slot);
+              if (n1 < n) bulk_g2s(dst + (uint32_t)n1 * kTok * 4, base, (uint32_t)(n - n1) * kTok * 4, bar_full + 8 * slot);
+            } else {
+              bulk_g2s(dst, base + (size_t)s * kMelRows * kTok, bytes, bar_full + 8 * slot);
+            }
             if (++slot == kRing) slot = 0, phase ^= 1;
           }
         }

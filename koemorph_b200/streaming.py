@@ -53,6 +53,7 @@ class StreamingEngine:
         self.n = 0                                          # hops pushed so far
         self.emitted = 0
         self._fe = model._frontend(self.dev)
+        self._alpha, self._alpha_key = 0.0, None
 
     def reset(self):
         for t in (self.tail, self.ring_f, self.ring_r, self.fmax_f, self.fmax_r, self.state):
@@ -103,7 +104,12 @@ class StreamingEngine:
                 self.expr.data_ptr(), self.out.data_ptr(), None, None, _lib.PRECISIONS[m.precision], st),
                 "koe_dual_stream_ring")
             if m.use_temporal_smoothing:
-                alpha = float(torch.sigmoid(m.smoothing_alpha.detach().float()))
+                # sigmoid(smoothing_alpha) is read back once per parameter version, not once per hop (a device sync)
+                ver = (m.smoothing_alpha.data_ptr(), m.smoothing_alpha._version)
+                if self._alpha_key != ver:
+                    self._alpha = float(torch.sigmoid(m.smoothing_alpha.detach().float()))
+                    self._alpha_key = ver
+                alpha = self._alpha
                 _lib.check(lib.koe_ema_scan(self.out.data_ptr(), self.S, 1, alpha, self.state.data_ptr(),
                                             1 if self.emitted > 0 else 0, st), "koe_ema_scan")
         self.emitted += 1
