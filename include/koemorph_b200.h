@@ -170,6 +170,10 @@ typedef struct {
   const void* tc_bf16;
   int32_t tc_stages;   /* number of 16 KiB stage images behind tc_bf16 */
   int32_t reserved_;
+  /* tcgen05 path: the affine parts around the LayerNorm are folded into the pre-tiled weights (bc rides in the first GEMM
+   * as weight row k_mel against a constant-one operand column; mel_norm.weight scales the columns of qk / wv; its bias
+   * drops out of the scores (softmax-invariant) and moves into this value bias): tc_bv = wv . mel_norm.bias + bv, [256] */
+  const float* tc_bv;
 } koe_core_weights;
 
 /*

@@ -31,6 +31,7 @@ class CoreWeightsStruct(C.Structure):
         ("we1_t", C.c_void_p), ("be1", C.c_void_p), ("eln_g", C.c_void_p), ("eln_b", C.c_void_p),
         ("we2_t", C.c_void_p), ("be2", C.c_void_p),
         ("tc_bf16", C.c_void_p), ("tc_stages", C.c_int32), ("reserved_", C.c_int32),
+        ("tc_bv", C.c_void_p),
     ]
 
 

@@ -48,7 +48,6 @@ constexpr int kPSbo = 10 * 128;                   // P / vT tiles: K = 80 -> 10 
 constexpr int kPTile = 16 * kPSbo;                // 20480
 constexpr int kStagesTile = 4;
 constexpr int kMelRows = 48;                      // mel rows (frames) per ring stage: 48 * 320 B = 15360 B, 6 K-chunks
-constexpr int kMelStageBytes = kMelRows * kTok * 4;
 
 // shared memory map (bytes)
 constexpr int kOffBar = 0;                        // mbarriers + tmem base
@@ -190,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 2));
   float* s_red = reinterpret_cast<float*>(smem + kOffBar + 8 * (2 * kRing + 2) + 16);  // [8]
   float* s_const = reinterpret_cast<float*>(smem + kOffConst);
-  const float *s_bc = s_const, *s_g = s_const + 256, *s_b = s_const + 512, *s_bv = s_const + 768;
+  const float* s_bv = s_const + 768;
   const float *s_ba = s_const + 1024, *s_w2 = s_const + 1152;
   float* s_ln = s_const + 1280;  // [stat 2][warpgroup 2][row 128]
 
@@ -205,10 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   }
   if (tid < kSimt) {
     for (int i = tid; i < 256; i += kSimt) {
-      s_const[i] = W.bc[i];
-      s_const[256 + i] = W.ln_g[i];
-      s_const[512 + i] = W.ln_b[i];
-      s_const[768 + i] = W.bv[i];
+      s_const[768 + i] = W.tc_bv[i];  // (bc, mel_norm.weight / bias are folded into the pre-tiled weights)
     }
     if (tid < 128) {
       s_const[1024 + tid] = W.ba[tid];
@@ -427,6 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int e = 0; e < 3; ++e) v[e] = normalise_bf16(extra[e], ref_db, true);
+          v[3] = 1.0f;  // operand column k_mel: multiplies the encoder-bias row of the weights
           *reinterpret_cast<uint4*>(arow + kLongChunks * 128) = pack8_bf16(v);
           *reinterpret_cast<uint4*>(arow + (kLongChunks + 1) * 128) = make_uint4(0, 0, 0, 0);
           // edge frames inside the long-term range see zeros beyond the window edge: patch them in place
@@ -491,12 +488,14 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
               if (prenorm) {
                 v[0][e] = r[e].x, v[1][e] = r[e].y, v[2][e] = r[e].z, v[3][e] = r[e].w;
               } else {
-                const bool real = 8 * c + e < kKMel;       // K tail 259..271 must be exact zeros
+                const bool real = 8 * c + e < kKMel;       // the K tail past the bias column must be exact zeros
                 v[0][e] = real ? normalise_bf16(r[e].x, ref_db, true) : 0.0f;
                 v[1][e] = real ? normalise_bf16(r[e].y, ref_db, true) : 0.0f;
                 v[2][e] = real ? normalise_bf16(r[e].z, ref_db, true) : 0.0f;
                 v[3][e] = real ? normalise_bf16(r[e].w, ref_db, true) : 0.0f;
               }
+              if (8 * c + e == kKMel)  // operand column k_mel: multiplies the encoder-bias row of the weights
+                v[0][e] = v[1][e] = v[2][e] = v[3][e] = 1.0f;
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -533,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
             tmem_ld32(lane_taddr + kColD1 + cb + c0, v);
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              const float x0 = v[i] + s_bc[cb + c0 + i], x1 = v[i + 1] + s_bc[cb + c0 + i + 1];
+              const float x0 = v[i], x1 = v[i + 1];  // (the encoder bias came in through the GEMM)
               s0 += x0, s1 += x1;
               q0 = fmaf(x0, x0, q0), q1 = fmaf(x1, x1, q1);
             }
@@ -545,14 +544,14 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         if (live) {
           const float mean = (s_ln[row] + s_ln[128 + row]) * (1.0f / 256);
           const float var = fmaxf((s_ln[256 + row] + s_ln[384 + row]) * (1.0f / 256) - mean * mean, 0.0f);
-          const float rstd = rsqrtf(var + W.ln_eps);
+          const float rstd = rsqrtf(var + W.ln_eps), shift = -mean * rstd;
           unsigned char* erow = smem + kOffE + (row >> 3) * kESbo + (row & 7) * 16;
           for (int c0 = 0; c0 < 128; c0 += 32) {
             float v[32];
             tmem_ld32(lane_taddr + kColD1 + cb + c0, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              v[i] = (v[i] + s_bc[cb + c0 + i] - mean) * rstd * s_g[cb + c0 + i] + s_b[cb + c0 + i];
+              v[i] = fmaf(v[i], rstd, shift);  // normalised only: mel_norm.weight / bias live in the qk / wv weights
             if (row < kTok) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
@@ -703,7 +702,7 @@ int launch_dual_stream_tc(const CoreParams& p, int precision, cudaStream_t strea
   if (p.w.k_mel != 259 && p.w.k_mel != 515)
     return fail(KOE_E_UNSUPPORTED, "tensor-core path is built for k_mel = 259 (30 fps) and 515 (60 fps); got %d", p.w.k_mel);
   const int need_stages = p.w.k_mel == 259 ? tc::Geo<259>::kStagesPerWindow : tc::Geo<515>::kStagesPerWindow;
-  if (p.w.tc_bf16 == nullptr || p.w.tc_stages != need_stages)
+  if (p.w.tc_bf16 == nullptr || p.w.tc_bv == nullptr || p.w.tc_stages != need_stages)
     return fail(KOE_E_INVALID, "tensor-core path: koe_core_weights.tc_bf16 is missing (%d stages, need %d)",
                 p.w.tc_stages, need_stages);
   static int num_sms[64] = {0};

@@ -66,6 +66,7 @@ class CoreWeights:
         tc = tensors.get("tc_bf16")
         s.tc_bf16 = tc.data_ptr() if tc is not None else None
         s.tc_stages = 0 if tc is None else tc.numel() * 2 // TC_STAGE_BYTES
+        s.tc_bv = tensors["tc_bv"].data_ptr() if "tc_bv" in tensors else None
         self.struct = s
         self.device = tensors["wc_t"].device
 
@@ -134,12 +135,20 @@ def fold(sd: Dict[str, torch.Tensor], num_heads: int, temperature: float, device
     if k_mel in (259, 515):
         # tcgen05 path: stage images in consumption order -- Wc (9 x [256 x 32] at 30 fps, 17 at 60 fps), Qk tiles 0/1,
         # Wv tiles 0/1, Wa (each 4 x [128 x 64]); Qk rows are re-indexed to 32*h + q (queries 28..31 of each head are zero rows)
+        # The affine parts around the LayerNorm are folded away (in float64, like everything here): the encoder bias is
+        # weight column k_mel of the first GEMM (the kernel puts a constant one in that operand column); mel_norm.weight
+        # scales the input columns of the key and value projections; mel_norm.bias adds a per-(head, query) constant to
+        # the scores, which the softmax ignores, and Wv . bias to the values, which joins the value bias (tc_bv).
+        ln_g, ln_b = g("mel_norm.weight"), g("mel_norm.bias")
         qk_pad = torch.zeros(256, d, dtype=dd, device=device)
         for h in range(num_heads):
-            qk_pad[32 * h:32 * h + nq] = qk[h * nq:(h + 1) * nq]
+            qk_pad[32 * h:32 * h + nq] = qk[h * nq:(h + 1) * nq] * ln_g
+        wc_b = torch.cat([wc, bc.reshape(-1, 1)], dim=1)          # [256, k_mel + 1]
+        assert k_mel + 1 <= _ceil_to(k_mel, 16)
+        tensors["tc_bv"] = f32(wv @ ln_b + bv)
         n_g1 = (_ceil_to(k_mel, 16) + 31) // 32
-        stages = _tile_kmajor(wc, 256, 32, 32 * n_g1) + _tile_kmajor(qk_pad, 128, 64, 256) + \
-            _tile_kmajor(wv, 128, 64, 256) + _tile_kmajor(wa, 128, 64, 256)
+        stages = _tile_kmajor(wc_b, 256, 32, 32 * n_g1) + _tile_kmajor(qk_pad, 128, 64, 256) + \
+            _tile_kmajor(wv * ln_g, 128, 64, 256) + _tile_kmajor(wa, 128, 64, 256)
         tensors["tc_bf16"] = torch.cat(stages).to(torch.bfloat16).contiguous()
         assert tensors["tc_bf16"].numel() * 2 == (n_g1 + 20) * TC_STAGE_BYTES
     b2 = float(sd["blendshape_decoder.3.bias"].detach().reshape(-1)[0])
