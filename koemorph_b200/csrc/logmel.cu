@@ -172,7 +172,7 @@ __device__ __forceinline__ void load_interior(const LogmelParams& p, const PairI
   const float* __restrict__ pa = clip + pi.fa_lo + lane;
   const float* __restrict__ pb = clip + pi.fb_lo + lane;
 #pragma unroll
-  for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = make_float2(__ldg(pa + 32 * n1), __ldg(pb + 32 * n1));
+  for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = make_float2(__ldcs(pa + 32 * n1), __ldcs(pb + 32 * n1));  // streaming: evict-first in L2
 }
 
 // frames that touch a clip / window edge (~2 pairs per clip): masked or reflected samples, staged through the warp's
