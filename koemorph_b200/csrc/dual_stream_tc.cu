@@ -97,6 +97,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!ok && spin > (1u << 22)) __trap();
   }
 }
+// L2 cache policies for the bulk copies: the weights are re-read by every window of every step (keep), a window's mel
+// rows are read once (let them go first)
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -237,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
     if (lane == 0) {
       const unsigned char* src = reinterpret_cast<const unsigned char*>(W.tc_bf16);
       uint32_t slot = 0, phase = 0;
+      const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         if (tma_mel) {
           // the window's plain mel rows [0, Tl) are contiguous in HBM: stream them through the same ring, ahead of the
@@ -255,10 +274,12 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
             if (p.ring_frames > 0) {
               const int r0 = (p.ring_base + kMelRows * s) % p.ring_frames;
               const int n1 = min(n, p.ring_frames - r0);
-              bulk_g2s(dst, base + (size_t)r0 * kTok, (uint32_t)n1 * kTok * 4, bar_full + 8 * slot);
-              if (n1 < n) bulk_g2s(dst + (uint32_t)n1 * kTok * 4, base, (uint32_t)(n - n1) * kTok * 4, bar_full + 8 * slot);
+              bulk_g2s_hint(dst, base + (size_t)r0 * kTok, (uint32_t)n1 * kTok * 4, bar_full + 8 * slot, pol_keep);
+              if (n1 < n)
+                bulk_g2s_hint(dst + (uint32_t)n1 * kTok * 4, base, (uint32_t)(n - n1) * kTok * 4, bar_full + 8 * slot, pol_keep);
             } else {
-              bulk_g2s(dst, base + (size_t)s * kMelRows * kTok, bytes, bar_full + 8 * slot);
+              bulk_g2s_hint(dst, base + (size_t)s * kMelRows * kTok, bytes, bar_full + 8 * slot,
+                            p.n_out > 1 ? pol_keep : pol_stream);  // overlapping windows of a sequence re-read their rows
             }
             if (++slot == kRing) slot = 0, phase ^= 1;
           }
@@ -266,8 +287,8 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         for (int s = 0; s < kStagesPerWindow; ++s) {
           mbar_wait(bar_empty + 8 * slot, phase ^ 1);
           mbar_expect_tx(bar_full + 8 * slot, kStageBytes);
-          bulk_g2s(sbase + kOffRing + slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
-                   bar_full + 8 * slot);
+          bulk_g2s_hint(sbase + kOffRing + slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
+                        bar_full + 8 * slot, pol_keep);
           if (++slot == kRing) slot = 0, phase ^= 1;
         }
       }
