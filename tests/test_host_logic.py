@@ -119,3 +119,13 @@ def test_c_abi_exports_every_declared_symbol():
     assert not missing, f"library does not export {missing}"
     assert set(_lib.exported_symbols()) <= set(declared)
     assert lib.koe_version() >= 100
+
+
+def test_numa_binding_helper_is_a_no_op_without_topology():
+    """bind_host_thread_to_gpu_node must never raise: without a GPU / sysfs topology it returns None and leaves the
+    affinity mask alone."""
+    from koemorph_b200.infer import bind_host_thread_to_gpu_node
+    before = os.sched_getaffinity(0)
+    assert bind_host_thread_to_gpu_node(0) in (None, 0, 1, 2, 3)
+    if not __import__("torch").cuda.is_available():
+        assert os.sched_getaffinity(0) == before
