@@ -123,6 +123,14 @@ typedef struct {
 int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_args* args, void* stream);
 
 /*
+ * 16-bit PCM -> float32 audio, sample / 32768: the normalisation libsndfile applies when the reference's loaders read a
+ * WAV file as float (sf.read(path, dtype="float32"), src/data/io.py:71, src/data/sequential_dataset.py:99).  Lets a host
+ * application hand the samples over as stored on disk, halving the PCIe bytes of the host-buffer path; the result is
+ * bit-identical to converting on the host.  Both buffers 16-byte aligned, n_samples counts samples over all clips.
+ */
+int koe_pcm16_to_float(const int16_t* pcm, int64_t n_samples, float* audio, void* stream);
+
+/*
  * Rest of power_to_db on koe_logmel_power's output (ref = max over the clip's n_frames frames, top_db=80), then (x+80)/80.
  * Writes the long-term features [n_clips][n_frames][80] and the short-term detail = last three frames
  * [n_clips][3][80] (zero rows when n_frames < 3: simplified_dual_stream_model.py:206-212).

@@ -870,3 +870,45 @@ extern "C" int koe_logmel_normalise(const float* power, const float* frame_max, 
   KOE_CUDA(cudaGetLastError());
   return KOE_OK;
 }
+
+// ---- 16-bit PCM host format: what a WAV file holds; halves the PCIe bytes of the host-buffer path ----------------------
+namespace koe {
+// eight samples per thread per step: one 16-byte load, two 16-byte streaming stores
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const int16_t* __restrict__ pcm, long long n,
+                                                              float* __restrict__ audio) {
+  constexpr float kScale = 1.0f / 32768.0f;  // libsndfile's int16 -> float normalisation (sf.read(dtype="float32"))
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int4 w = __ldcs(reinterpret_cast<const int4*>(pcm) + i);
+    const int word[4] = {w.x, w.y, w.z, w.w};
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f[2 * k] = (float)(short)(word[k] & 0xffff) * kScale;
+      f[2 * k + 1] = (float)(word[k] >> 16) * kScale;
+    }
+    float4* dst = reinterpret_cast<float4*>(audio) + 2 * i;
+    dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+    dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) audio[(n8 << 3) + threadIdx.x] = (float)pcm[(n8 << 3) + threadIdx.x] * kScale;
+}
+}  // namespace koe
+
+extern "C" int koe_pcm16_to_float(const int16_t* pcm, int64_t n_samples, float* audio, void* stream) {
+  KOE_REQUIRE(n_samples >= 0, "koe_pcm16_to_float: negative size");
+  if (n_samples == 0) return KOE_OK;
+  KOE_REQUIRE(pcm != nullptr && audio != nullptr, "koe_pcm16_to_float: NULL argument");
+  KOE_REQUIRE(((reinterpret_cast<uintptr_t>(pcm) | reinterpret_cast<uintptr_t>(audio)) & 15) == 0,
+              "koe_pcm16_to_float: buffers must be 16-byte aligned");
+  int dev = 0, sms = 0;
+  KOE_CUDA(cudaGetDevice(&dev));
+  KOE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long want = ((n_samples >> 3) + 255) / 256;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * 8));
+  koe::pcm16_to_float_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pcm, (long long)n_samples, audio);
+  koe::count_launch();
+  KOE_CUDA(cudaGetLastError());
+  return KOE_OK;
+}

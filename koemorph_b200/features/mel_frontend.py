@@ -18,6 +18,22 @@ N_FFT = 1024
 N_MELS = 80
 
 
+def pcm16_to_float(pcm: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int16 PCM on the device -> float32 audio, sample / 32768 (what sf.read(dtype="float32") returns for a 16-bit WAV,
+    src/data/io.py:71); `out` may be a preallocated float32 tensor of the same shape."""
+    pcm = _lib.require_cuda(pcm, "pcm", torch.int16)
+    if out is None:
+        out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+    else:
+        out = _lib.require_cuda(out, "out")
+        if out.shape != pcm.shape:
+            raise ValueError(f"out has shape {tuple(out.shape)}, pcm {tuple(pcm.shape)}")
+    with torch.cuda.device(pcm.device):
+        _lib.check(_lib.load().koe_pcm16_to_float(pcm.data_ptr(), pcm.numel(), out.data_ptr(),
+                                                  _lib.stream_ptr(pcm.device)), "koe_pcm16_to_float")
+    return out
+
+
 class LogMelFrontend:
     """One handle (Hann window, FFT twiddles, sparse Slaney filterbank) per CUDA device."""
 

@@ -4,12 +4,18 @@ This is the call an application makes when its audio lives in host memory (the r
 convention is host numpy -> per-clip librosa, src/model/simplified_dual_stream_model.py:184-229).
 Clips are independent, so the batch is cut into chunks that flow through a two-stage pipeline on two CUDA
 streams: while chunk i runs the kernels, chunk i+1 is crossing PCIe.
+
+The audio may also be handed over as int16 PCM, the format the samples have in a WAV file (the reference's loaders turn
+it into float32 / 32768 on the host, src/data/io.py:71): PCIe then carries half the bytes and the conversion runs on the
+device (koe_pcm16_to_float), with bit-identical results.
 """
 from __future__ import annotations
 
 from typing import Optional
 
 import torch
+
+from .features.mel_frontend import pcm16_to_float
 
 
 def bind_host_thread_to_gpu_node(device_index: int) -> Optional[int]:
@@ -64,13 +70,22 @@ class HostPipeline:
         a, e = self._bufs[key]
         return a[:n], e[:n]
 
+    def _pcm_buffer(self, slot: int, n: int, L: int):
+        key = (slot, L, "pcm16")
+        if key not in self._bufs:
+            self._bufs[key] = torch.empty(self.chunk, L, dtype=torch.int16, device=self.device)
+        return self._bufs[key][:n]
+
     @torch.no_grad()
     def __call__(self, audio_host: torch.Tensor, egemaps_host: torch.Tensor,
                  out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """audio_host (B, L) float32 and egemaps_host (B, 264) in (ideally pinned) host memory ->
-        (B, T_out, 52) host tensor.  Synchronises before returning."""
+        """audio_host (B, L) float32 -- or int16 PCM, see the module docstring -- and egemaps_host (B, 264) in (ideally
+        pinned) host memory -> (B, T_out, 52) host tensor.  Synchronises before returning."""
         if audio_host.is_cuda or egemaps_host.is_cuda:
             raise ValueError("HostPipeline takes host tensors; call the model directly for device tensors")
+        if audio_host.dtype not in (torch.float32, torch.int16):
+            raise ValueError(f"audio_host must be float32 or int16 PCM, got {audio_host.dtype}")
+        pcm = audio_host.dtype == torch.int16
         B, L = audio_host.shape
         eg = egemaps_host.reshape(B, 264)
         n_out = self.model.num_output_frames(L) if hasattr(self.model, "num_output_frames") else None
@@ -85,7 +100,12 @@ class HostPipeline:
             s = self._streams[ci & 1]
             a_dev, e_dev = self._buffers(ci & 1, n, L)
             with torch.cuda.stream(s):
-                a_dev.copy_(audio_host[c0:c0 + n], non_blocking=True)
+                if pcm:
+                    p_dev = self._pcm_buffer(ci & 1, n, L)
+                    p_dev.copy_(audio_host[c0:c0 + n], non_blocking=True)
+                    pcm16_to_float(p_dev, a_dev)
+                else:
+                    a_dev.copy_(audio_host[c0:c0 + n], non_blocking=True)
                 e_dev.copy_(eg[c0:c0 + n], non_blocking=True)
                 res = self.model(a_dev, egemaps=e_dev)["blendshapes"]
                 out_host[c0:c0 + n].copy_(res, non_blocking=True)

@@ -308,3 +308,34 @@ def test_bf16_unsupported_geometry_is_refused_not_faked(K):
     m.precision = "bf16"
     with pytest.raises(RuntimeError, match="tc_bf16 is missing|30 fps"):
         m(torch.zeros(1, 136000, device="cuda"), egemaps=torch.zeros(1, 264, device="cuda"))
+
+
+def test_pcm16_conversion_is_exact_and_host_pipeline_accepts_it(K):
+    """int16 PCM -> float is sample / 32768 (libsndfile's normalisation behind sf.read(dtype="float32"),
+    src/data/io.py:71), bit for bit, including the < 8-sample tail; the host-buffer pipeline fed int16 returns exactly
+    what it returns for the same samples as float32."""
+    from koemorph_b200.features.mel_frontend import pcm16_to_float
+    from koemorph_b200.infer import HostPipeline
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 8, 4099, 136000 * 3 + 5):
+        pcm = rng.integers(-32768, 32768, size=n, dtype=np.int16)
+        if n >= 2:
+            pcm[0], pcm[-1] = -32768, 32767
+        got = pcm16_to_float(torch.from_numpy(pcm).cuda()).cpu().numpy()
+        assert np.array_equal(got, pcm.astype(np.float32) / np.float32(32768.0))
+    with pytest.raises(TypeError):
+        pcm16_to_float(torch.zeros(8, device="cuda"))
+
+    spec = dict(wseed=3, fps=30, style="stress", B=5, L=136000, iseed=11, kind="speechlike")
+    m, _ = _model(K, spec, sequential=True)
+    audio, eg = O.make_inputs(spec["iseed"], spec["B"], spec["L"], spec["kind"])
+    pcm = np.clip(np.round(audio * 32768.0), -32768, 32767).astype(np.int16)
+    as_float = torch.from_numpy(pcm.astype(np.float32) / np.float32(32768.0))
+    pipe = HostPipeline(m, chunk_clips=2)  # 3 chunks, the last one ragged
+    want = pipe(as_float.pin_memory(), torch.from_numpy(eg).pin_memory()).clone()
+    got = pipe(torch.from_numpy(pcm).pin_memory(), torch.from_numpy(eg).pin_memory())
+    assert torch.equal(got, want)
+    ref = m(as_float.cuda(), egemaps=torch.from_numpy(eg).cuda())["blendshapes"].cpu()
+    assert torch.equal(want, ref)
+    with pytest.raises(ValueError):
+        pipe(torch.zeros(2, 136000, dtype=torch.float64), torch.from_numpy(eg[:2]))
