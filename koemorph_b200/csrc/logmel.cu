@@ -143,8 +143,26 @@ __device__ __forceinline__ PairInfo locate_pair(const LogmelParams& p, unsigned 
   pi.frame = -1;
   pi.interior = false;
   if (pair >= total_pairs) return pi;
-  const int b = (int)(pair / ppc);
-  const int ga = 2 * (int)(pair - (unsigned)b * ppc);
+  // Launch order of the pairs: every clip's first pair, then every clip's last pair, then the middle ones clip by clip.
+  // The first / last pairs are the ones that touch the padding and take the masked loads (~25 % more instructions for
+  // that warp); grouped, they fill whole 16-warp iterations instead of holding 15 interior warps at the barrier in one
+  // iteration out of five.
+  int b, j;
+  if (ppc <= 2) {
+    b = (int)(pair / ppc);
+    j = (int)(pair - (unsigned)b * ppc);
+  } else if (pair < (unsigned)p.n_clips) {
+    b = (int)pair;
+    j = 0;
+  } else if (pair < 2u * (unsigned)p.n_clips) {
+    b = (int)pair - p.n_clips;
+    j = (int)ppc - 1;
+  } else {
+    const unsigned r = pair - 2u * (unsigned)p.n_clips;
+    b = (int)(r / (ppc - 2));
+    j = 1 + (int)(r - (unsigned)b * (ppc - 2));
+  }
+  const int ga = 2 * j;
   pi.clip = b;
   pi.frame = ga;
   pi.has_b = ga + 1 < p.n_frames;
@@ -175,26 +193,29 @@ __device__ __forceinline__ void load_interior(const LogmelParams& p, const PairI
   for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = make_float2(__ldcs(pa + 32 * n1), __ldcs(pb + 32 * n1));  // streaming: evict-first in L2
 }
 
-// frames that touch a clip / window edge (~2 pairs per clip): masked or reflected samples, staged through the warp's
-// shared-memory tile as tile[n1 * 32 + lane] = (a, b); out of line and not unrolled to keep the hot loop small
-__device__ __noinline__ void load_edge(const float* __restrict__ clip, int n_samples, int pad_mode, int fa_lo, int fb_lo,
-                                       int lo_a, int hi_a, int lo_b, int hi_b, float2* tile) {
-  const int lane = threadIdx.x & 31;
-  const int last = n_samples - 1;
-#pragma unroll 1
+// frames that touch a clip / window edge (~2 pairs per clip): masked or reflected samples, loaded into the same registers
+// one iteration ahead like the interior ones (an edge pair that fetched its samples at the start of its own transform held
+// the other 15 warps of the iteration at the barrier for the length of 32 dependent global loads)
+__device__ __forceinline__ void load_edge(const LogmelParams& p, const PairInfo& pi, int lane, float2 (&v)[32]) {
+  const float* __restrict__ clip = p.audio + (long long)pi.clip * p.audio_stride;
+  const int last = p.n_samples - 1;
+  const bool reflect = p.pad_mode == 1;  // numpy "reflect" padding about the first / last sample (MelSlidingWindowExtractor default)
+  const bool b_on = pi.hi_b > pi.lo_b;
+  const int sa0 = pi.fa_lo + lane, sb0 = pi.fb_lo + lane;
+#pragma unroll
   for (int n1 = 0; n1 < 32; ++n1) {
-    int sa = fa_lo + lane + 32 * n1, sb = fb_lo + lane + 32 * n1;
+    int sa = sa0 + 32 * n1, sb = sb0 + 32 * n1;
     bool oka, okb;
-    if (pad_mode == 1) {  // numpy "reflect" padding about the first / last sample (MelSlidingWindowExtractor default)
+    if (reflect) {
       sa = sa < 0 ? -sa : (sa > last ? 2 * last - sa : sa);
       sb = sb < 0 ? -sb : (sb > last ? 2 * last - sb : sb);
       oka = sa >= 0 && sa <= last;
-      okb = hi_b > lo_b && sb >= 0 && sb <= last;
+      okb = b_on && sb >= 0 && sb <= last;
     } else {
-      oka = sa >= lo_a && sa < hi_a;
-      okb = sb >= lo_b && sb < hi_b;
+      oka = sa >= pi.lo_a && sa < pi.hi_a;
+      okb = sb >= pi.lo_b && sb < pi.hi_b;
     }
-    tile[n1 * 32 + lane] = make_float2(oka ? __ldg(clip + sa) : 0.0f, okb ? __ldg(clip + sb) : 0.0f);
+    v[bitrev5(n1)] = make_float2(oka ? __ldcs(clip + sa) : 0.0f, okb ? __ldcs(clip + sb) : 0.0f);
   }
 }
 
@@ -323,19 +344,12 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   unsigned it = blockIdx.x;
   PairInfo nxt = locate_pair(p, it < n_iters ? it * kWarps + warp : total_pairs, total_pairs, ppc);
   if (nxt.interior) load_interior(p, nxt, lane, v);
+  else if (nxt.frame >= 0) load_edge(p, nxt, lane, v);
 
   for (; it < n_iters; it += gridDim.x) {
     // ------------------------------------------------------------------ FFT phase (per warp)
     const PairInfo cur = nxt;
     if (cur.frame >= 0) {
-      if (!cur.interior) {
-        load_edge(p.audio + (long long)cur.clip * p.audio_stride, p.n_samples, p.pad_mode, cur.fa_lo, cur.fb_lo, cur.lo_a,
-                  cur.hi_a, cur.lo_b, cur.hi_b, xb2);
-        __syncwarp();
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = xb2[n1 * 32 + lane];
-        __syncwarp();
-      }
 #pragma unroll
       for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = __fmul2_rn(v[bitrev5(n1)], bcast(s_hann[32 * n1 + lane]));
       fft32(v);  // v[k1] = Y[k1] of column n2 = lane
@@ -393,6 +407,7 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
     // audio of the next iteration: in flight during the filterbank / store phases
     nxt = locate_pair(p, it + gridDim.x < n_iters ? (it + gridDim.x) * kWarps + warp : total_pairs, total_pairs, ppc);
     if (nxt.interior) load_interior(p, nxt, lane, v);
+    else if (nxt.frame >= 0) load_edge(p, nxt, lane, v);
     __syncthreads();
 
     // ------------------------------------------------------------------ mel phase: lane = frame slot, warp = run of bins
