@@ -26,10 +26,12 @@ namespace koe {
 
 namespace tc {
 
-constexpr int kThreads = 320;   // warps 0-7 SIMT (two warpgroups), warp 8 TMA producer, warp 9 MMA issuer
+constexpr int kThreads = 352;   // warps 0-7 SIMT (two warpgroups), warp 8 weight producer, warp 9 MMA issuer, warp 10 mel-row producer
 constexpr int kSimt = 256;
 constexpr int kStageBytes = 16384;
-constexpr int kRing = 6;             // 16 KiB stages; 6 so that the next window's mel rows prefetch behind the last weight stages
+constexpr int kRing = 6;             // 16 KiB stages: slots [0, kWRing) carry weights (consumer: the MMA warp), slots [kWRing, kRing)
+constexpr int kWRing = 4;            // the windows' mel rows (consumer: the SIMT warps).  Two rings, two producers: a slow consumer of
+                                     // one kind never holds up the other kind's stages, as it did when both shared one FIFO
 constexpr int kTok = 80;
 // Window geometry: K of the first GEMM = mel_sequence_length + 3 = 259 (30 fps) or 515 (60 fps)
 template <int KMEL>
@@ -37,10 +39,12 @@ struct Geo {
   static constexpr int kKMel = KMEL;
   static constexpr int kKMelPad = (KMEL + 15) / 16 * 16;        // 272 / 528
   static constexpr int kA1Chunks = kKMelPad / 8;                // 34 / 66 16-byte K chunks per row
-  static constexpr int kA1Sbo = kA1Chunks * 128;                // 4352 / 8448
+  static constexpr int kA1Sbo = kA1Chunks * 128 + 16;           // 4368 / 8464: row groups skewed by 16 B (shared-memory banks)
   static constexpr int kLongChunks = (KMEL - 3) / 8;            // 32 / 64 chunks of long-term frames, then the short-term chunk
   static constexpr int kStagesG1 = (kKMelPad + 31) / 32;        // 9 / 17 weight stages of [256 x 32]; the last is half full
   static constexpr int kStagesPerWindow = kStagesG1 + 20;       // + 5 x 4 stages of [128 x 64]
+  // the first-GEMM operand of window i+1 is staged while the S/VT GEMMs of window i run; needs the operand to fit the X region
+  static constexpr bool kStageAhead = KMEL == 259;
 };
 constexpr int kA1Sbo30 = Geo<259>::kA1Sbo;
 constexpr int kESbo = 32 * 128;                   // enc / Oflat: K = 256 -> 32 chunks
@@ -52,8 +56,9 @@ constexpr int kMelRows = 48;                      // mel rows (frames) per ring 
 // shared memory map (bytes)
 constexpr int kOffBar = 0;                        // mbarriers + tmem base
 constexpr int kOffConst = 256;                    // bc, ln_g, ln_b, bv (256 each), ba, w2 (128 each), LN partials (512)
-constexpr int kOffX = kOffConst + 1792 * 4;       // A1 (43520) / P tiles (40960)
-constexpr int kOffE = kOffX + 10 * kA1Sbo30;      // enc (40960) / Oflat; at 60 fps the A1 operand (84480 B) spans X and E, which is
+constexpr int kOffX = kOffConst + 1792 * 4;       // A1 (43520): free from the end of the first GEMM, so at 30 fps the NEXT
+                                                  // window's operand is staged here while the S/VT GEMMs of this one run
+constexpr int kOffE = kOffX + (10 * kA1Sbo30 + 127) / 128 * 128;      // enc (40960) -> P tiles (40960) -> Oflat; at 60 fps the A1 operand (84480 B) spans X and E, which is
                                                   // free until the LayerNorm epilogue writes enc after the first GEMM
 constexpr int kOffVT = kOffE + 10 * kESbo;        // vT tiles (40960)
 constexpr int kOffRing = kOffVT + 2 * kPTile;
@@ -63,7 +68,9 @@ static_assert(kOffX + 16 * Geo<515>::kA1Sbo <= kSmemBytes && kOffE + 16 * kESbo 
 static_assert(kOffX + 10 * Geo<515>::kA1Sbo <= kOffVT, "the 60 fps A1 operand ends where the vT tiles begin");
 
 // TMEM column map
-constexpr uint32_t kColD1 = 0, kColS = 256, kColVT = 0, kColO = 160, kColH = 0;
+constexpr uint32_t kColD1 = 0, kColS = 256, kColVT = 0, kColO = 160;
+// H sits clear of [0, 256): the next window's first GEMM runs while the decoder tail still reads it (O is consumed by then)
+constexpr uint32_t kColH = 288;
 
 // (dB - ref) clamped at -80 dB and rescaled to [0, 1], as normalise_db(., ., true) -- but the operand is rounded to bf16
 // next (2^-9 relative), so the exact fp32 division of the reference is replaced by one FFMA (<= 1 ulp of fp32 away)
@@ -119,6 +126,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -196,6 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   using G = Geo<KMEL>;
   constexpr int kKMel = G::kKMel, kA1Chunks = G::kA1Chunks, kA1Sbo = G::kA1Sbo, kLongChunks = G::kLongChunks;
   constexpr int kStagesG1 = G::kStagesG1, kStagesPerWindow = G::kStagesPerWindow;
+  constexpr bool kStageAhead = G::kStageAhead;
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -251,106 +265,135 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   const int n_mel_stages = tma_mel ? (Tl + kMelRows - 1) / kMelRows : 0;
 
   if (warp == 8) {
-    // =========================================================== TMA producer ==========================
+    // =========================================================== weight producer ========================
     if (lane == 0) {
       const unsigned char* src = reinterpret_cast<const unsigned char*>(W.tc_bf16);
       uint32_t slot = 0, phase = 0;
-      const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+      const uint64_t pol_keep = l2_policy_keep();
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        if (tma_mel) {
-          // the window's plain mel rows [0, Tl) are contiguous in HBM: stream them through the same ring, ahead of the
-          // weights, so that by the time the SIMT warps start a window its rows are already in shared memory
-          const int b = item / p.n_out, wi = item % p.n_out;
-          // linear buffer: rows [0, Tl) of the window are contiguous; ring: row k is slot (ring_base + k) % ring_frames of
-          // the stream's ring, i.e. at most two contiguous runs per stage
-          const float* base = p.ring_frames > 0 ? p.power[0] + (size_t)b * p.ring_frames * kTok
-                                                : p.power[0] + window_row(p, 0, b, wi, 0) * kTok;
-          for (int s = 0; s < n_mel_stages; ++s) {
-            const int n = min(kMelRows, Tl - kMelRows * s);
-            const uint32_t bytes = (uint32_t)n * kTok * 4;
-            const uint32_t dst = sbase + kOffRing + slot * kStageBytes;
-            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-            mbar_expect_tx(bar_full + 8 * slot, bytes);
-            if (p.ring_frames > 0) {
-              const int r0 = (p.ring_base + kMelRows * s) % p.ring_frames;
-              const int n1 = min(n, p.ring_frames - r0);
-              bulk_g2s_hint(dst, base + (size_t)r0 * kTok, (uint32_t)n1 * kTok * 4, bar_full + 8 * slot, pol_keep);
-              if (n1 < n)
-                bulk_g2s_hint(dst + (uint32_t)n1 * kTok * 4, base, (uint32_t)(n - n1) * kTok * 4, bar_full + 8 * slot, pol_keep);
-            } else {
-              bulk_g2s_hint(dst, base + (size_t)s * kMelRows * kTok, bytes, bar_full + 8 * slot,
-                            p.n_out > 1 ? pol_keep : pol_stream);  // overlapping windows of a sequence re-read their rows
-            }
-            if (++slot == kRing) slot = 0, phase ^= 1;
-          }
-        }
+        long long* dp = (p.dbg != nullptr && blockIdx.x == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 32 + 16 * (item / gridDim.x) : nullptr;
         for (int s = 0; s < kStagesPerWindow; ++s) {
           mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+          if (s >= kStagesPerWindow - 4) stamp(dp, s - (kStagesPerWindow - 4));
+          if (s == 0) stamp(dp, 4);
+          if (s == kStagesG1 - 1) stamp(dp, 5);
+          if (s == kStagesG1) stamp(dp, 6);
+          if (s == kStagesPerWindow - 5) stamp(dp, 7);
           mbar_expect_tx(bar_full + 8 * slot, kStageBytes);
           bulk_g2s_hint(sbase + kOffRing + slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
                         bar_full + 8 * slot, pol_keep);
-          if (++slot == kRing) slot = 0, phase ^= 1;
+          if (++slot == kWRing) slot = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // =========================================================== mel-row producer =======================
+    // a window's plain mel rows [0, Tl) are contiguous in HBM (linear buffer), or at most two runs per stage of a
+    // stream's ring (row k is slot (ring_base + k) % ring_frames); the SIMT warps stage them as the first GEMM's operand
+    if (lane == 0 && tma_mel) {
+      uint32_t slot = kWRing, phase = 0;
+      const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        long long* dp = (p.dbg != nullptr && blockIdx.x == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 32 + 16 * (item / gridDim.x) : nullptr;
+        const int b = item / p.n_out, wi = item % p.n_out;
+        const float* base = p.ring_frames > 0 ? p.power[0] + (size_t)b * p.ring_frames * kTok
+                                              : p.power[0] + window_row(p, 0, b, wi, 0) * kTok;
+        for (int s = 0; s < n_mel_stages; ++s) {
+          const int n = min(kMelRows, Tl - kMelRows * s);
+          const uint32_t bytes = (uint32_t)n * kTok * 4;
+          const uint32_t dst = sbase + kOffRing + slot * kStageBytes;
+          mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+          if (s == 0) stamp(dp, 8);
+          if (s == n_mel_stages - 1) stamp(dp, 9);
+          mbar_expect_tx(bar_full + 8 * slot, bytes);
+          if (p.ring_frames > 0) {
+            const int r0 = (p.ring_base + kMelRows * s) % p.ring_frames;
+            const int n1 = min(n, p.ring_frames - r0);
+            bulk_g2s_hint(dst, base + (size_t)r0 * kTok, (uint32_t)n1 * kTok * 4, bar_full + 8 * slot, pol_keep);
+            if (n1 < n)
+              bulk_g2s_hint(dst + (uint32_t)n1 * kTok * 4, base, (uint32_t)(n - n1) * kTok * 4, bar_full + 8 * slot, pol_keep);
+          } else {
+            bulk_g2s_hint(dst, base + (size_t)s * kMelRows * kTok, bytes, bar_full + 8 * slot,
+                          p.n_out > 1 ? pol_keep : pol_stream);  // overlapping windows of a sequence re-read their rows
+          }
+          if (++slot == kRing) slot = kWRing, phase ^= 1;
         }
       }
     }
   } else if (warp == 9) {
     // =========================================================== MMA issuer ============================
-    if (lane == 0) {
+    // The whole warp runs the loop (waits, slot bookkeeping, descriptor arithmetic are warp-uniform, so they live in
+    // uniform registers); one elected lane issues the tcgen05 instructions.  With a single active thread instead
+    // (`if (lane == 0)`) every UTCHMMA / UTCBAR sits in its own elect-and-branch loop fed by R2UR moves and a stage of
+    // four MMAs took ~490 cycles to issue against 225-256 cycles of tensor time (scripts/microbench/
+    // umma_operand_layout_rate.cu: the no-swizzle K-major operands themselves run at the M=128 floor).
+    {
       uint32_t slot = 0, phase = 0, go_phase = 0;
       const uint32_t ring = sbase + kOffRing;
+      auto advance = [&]() {
+        if (++slot == kWRing) slot = 0, phase ^= 1;
+      };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        long long* dm = (p.dbg != nullptr && blockIdx.x == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 64 + 16 * (item / gridDim.x) : nullptr;
-        for (int s = 0; s < n_mel_stages; ++s)  // ring slots consumed by the SIMT warps
-          if (++slot == kRing) slot = 0, phase ^= 1;
+        long long* dm = (p.dbg != nullptr && lane == 0 && blockIdx.x == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 64 + 16 * (item / gridDim.x) : nullptr;
         // ---- G1: 9 stages of [256 x 32] weights; the last stage carries K = 256..271 only
         mbar_wait(bar_go, go_phase), go_phase ^= 1;
         stamp(dm, 0);
         tc_fence_after();
         for (int s = 0; s < kStagesG1; ++s) {
           mbar_wait(bar_full + 8 * slot, phase);
+          if (s < 3) stamp(dm, 12 + s);
+          if (s == kStagesG1 - 1) stamp(dm, 15);
           tc_fence_after();
-          const int nk = s == kStagesG1 - 1 ? 1 : 2;
-          for (int j = 0; j < nk; ++j) {
-            const uint64_t a = smem_desc(sbase + kOffX + (s * 2 + j) * 256, 128, kA1Sbo);
-            const uint64_t b = smem_desc(ring + slot * kStageBytes + j * 256, 128, 4 * 128);
-            tc_mma_bf16(tmem + kColD1, a, b, idesc_bf16(128, 256), (s | j) != 0);
+          if (elect_one()) {
+            const uint64_t a = smem_desc(sbase + kOffX + s * 512, 128, kA1Sbo);
+            const uint64_t b = smem_desc(ring + slot * kStageBytes, 128, 4 * 128);
+            tc_mma_bf16(tmem + kColD1, a, b, idesc_bf16(128, 256), s != 0);
+            if (s != kStagesG1 - 1) tc_mma_bf16(tmem + kColD1, a + (256 >> 4), b + (256 >> 4), idesc_bf16(128, 256), 1);
+            tc_commit(bar_empty + 8 * slot);
+            if (s == kStagesG1 - 1) tc_commit(bar_done);
           }
-          tc_commit(bar_empty + 8 * slot);
-          if (++slot == kRing) slot = 0, phase ^= 1;
+          __syncwarp();
+          advance();
         }
-        tc_commit(bar_done);
         stamp(dm, 1);
         // ---- S (2 tiles) and VT (2 tiles): A = weight stage [128 x 64], B = enc [80 x 256]
         mbar_wait(bar_go, go_phase), go_phase ^= 1;
         stamp(dm, 2);
         tc_fence_after();
-        for (int tile = 0; tile < 4; ++tile) {
+        for (int js = 0; js < 4 * kStagesTile; ++js) {
+          const int tile = js >> 2, s = js & 3;
           const uint32_t d = tmem + (tile < 2 ? kColS + 80 * tile : kColVT + 80 * (tile - 2));
-          for (int s = 0; s < kStagesTile; ++s) {
-            mbar_wait(bar_full + 8 * slot, phase);
-            tc_fence_after();
-            for (int j = 0; j < 4; ++j) {
-              const uint64_t a = smem_desc(ring + slot * kStageBytes + j * 256, 128, 8 * 128);
-              const uint64_t b = smem_desc(sbase + kOffE + (s * 4 + j) * 256, 128, kESbo);
-              tc_mma_bf16(d, a, b, idesc_bf16(128, 80), (s | j) != 0);
-            }
+          mbar_wait(bar_full + 8 * slot, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a = smem_desc(ring + slot * kStageBytes, 128, 8 * 128);
+            const uint64_t b = smem_desc(sbase + kOffE + s * 1024, 128, kESbo);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              tc_mma_bf16(d, a + j * (256 >> 4), b + j * (256 >> 4), idesc_bf16(128, 80), (s | j) != 0);
             tc_commit(bar_empty + 8 * slot);
-            if (++slot == kRing) slot = 0, phase ^= 1;
+            if (js == 4 * kStagesTile - 1) tc_commit(bar_done);
           }
+          __syncwarp();
+          advance();
         }
-        tc_commit(bar_done);
         stamp(dm, 3);
         // ---- PV: A = P tile [128 x 80], B = vT tile [128 x 80]
         mbar_wait(bar_go, go_phase), go_phase ^= 1;
         stamp(dm, 4);
         tc_fence_after();
-        for (int t = 0; t < 2; ++t)
-          for (int j = 0; j < 5; ++j) {
-            const uint64_t a = smem_desc(sbase + kOffX + t * kPTile + j * 256, 128, kPSbo);
-            const uint64_t b = smem_desc(sbase + kOffVT + t * kPTile + j * 256, 128, kPSbo);
-            tc_mma_bf16(tmem + kColO + 128 * t, a, b, idesc_bf16(128, 128), j != 0);
+        if (elect_one()) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint64_t a = smem_desc(sbase + kOffE + t * kPTile, 128, kPSbo);
+            const uint64_t b = smem_desc(sbase + kOffVT + t * kPTile, 128, kPSbo);
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+              tc_mma_bf16(tmem + kColO + 128 * t, a + j * (256 >> 4), b + j * (256 >> 4), idesc_bf16(128, 128), j != 0);
           }
-        tc_commit(bar_done);
+          tc_commit(bar_done);
+        }
+        __syncwarp();
         stamp(dm, 5);
         // ---- H1: A = Oflat [128(28) x 256], B = weight stage [128 x 64]
         mbar_wait(bar_go, go_phase), go_phase ^= 1;
@@ -358,16 +401,20 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         tc_fence_after();
         for (int s = 0; s < kStagesTile; ++s) {
           mbar_wait(bar_full + 8 * slot, phase);
+          stamp(dm, 8 + s);
           tc_fence_after();
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t a = smem_desc(sbase + kOffE + (s * 4 + j) * 256, 128, kESbo);
-            const uint64_t b = smem_desc(ring + slot * kStageBytes + j * 256, 128, 8 * 128);
-            tc_mma_bf16(tmem + kColH, a, b, idesc_bf16(128, 128), (s | j) != 0);
+          if (elect_one()) {
+            const uint64_t a = smem_desc(sbase + kOffE + s * 1024, 128, kESbo);
+            const uint64_t b = smem_desc(ring + slot * kStageBytes, 128, 8 * 128);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              tc_mma_bf16(tmem + kColH, a + j * (256 >> 4), b + j * (256 >> 4), idesc_bf16(128, 128), (s | j) != 0);
+            tc_commit(bar_empty + 8 * slot);
+            if (s == kStagesTile - 1) tc_commit(bar_done);
           }
-          tc_commit(bar_empty + 8 * slot);
-          if (++slot == kRing) slot = 0, phase ^= 1;
+          __syncwarp();
+          advance();
         }
-        tc_commit(bar_done);
         stamp(dm, 7);
       }
     }
@@ -375,15 +422,14 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
     // =========================================================== SIMT warps 0-7 ========================
     // warpgroup wg = warp / 4; warps w and w + 4 both own TMEM lanes 32 (w % 4) .. +31, so the two warpgroups split
     // every epilogue between them (LayerNorm: column halves; softmax / vT / O: one tile of 4 heads each)
-    uint32_t done_phase = 0, slot = 0, phase = 0;
+    uint32_t done_phase = 0, slot = kWRing, phase = 0;  // (slot, phase): the mel-row ring
     const int wg = warp >> 2, wq = warp & 3;
     const int row = 32 * wq + lane;                                        // TMEM lane == accumulator row
     const uint32_t lane_taddr = tmem + ((uint32_t)(32 * wq) << 16);
     const bool prenorm = p.mel_long != nullptr;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // first-GEMM operand of one window: dB reference, normalise, bf16, K-major core matrices in the X region
+    auto stage_window = [&](const int item, long long* ds) {
       const int b = item / p.n_out, wi = item % p.n_out;
-      long long* ds = (p.dbg != nullptr && blockIdx.x == 0 && tid == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 16 * (item / gridDim.x) : nullptr;
-      stamp(ds, 0);
       // ---- window dB reference
       float ref_db = 0.0f;
       if (!prenorm) {
@@ -399,6 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
                        fmaxf(fmaxf(s_red[4], s_red[5]), fmaxf(s_red[6], s_red[7])));
         simt_barrier();
       }
+      stamp(ds, 10);
       if (tma_mel) {
         // ---- A1 from the TMA-staged rows: Xn[channel j][time t] as bf16, one 16-byte store = 8 frames of a channel
         // rows that are not plain frames of this window (short-term detail, edge variants) are fetched directly, early
@@ -431,11 +478,12 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
                 pack8_bf16(v);
           }
           simt_barrier();                                   // every thread is done reading this ring slot
+          if (s == 0) stamp(ds, 11);
+          if (s == 2) stamp(ds, 12);
+          if (s == n_mel_stages - 1) stamp(ds, 13);
           if (tid == 0) mbar_arrive(bar_empty + 8 * slot);
-          if (++slot == kRing) slot = 0, phase ^= 1;
+          if (++slot == kRing) slot = kWRing, phase ^= 1;
         }
-        for (int s = 0; s < kStagesPerWindow; ++s)          // the weight stages belong to the MMA thread
-          if (++slot == kRing) slot = 0, phase ^= 1;
         if (tid < kTok) {
           const int j = tid;
           unsigned char* arow = smem + kOffX + (j >> 3) * kA1Sbo + (j & 7) * 16;
@@ -534,8 +582,22 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           }
         }
       }
+    };
+    if (kStageAhead && (int)blockIdx.x < n_items) {
+      stage_window(blockIdx.x, nullptr);
       fence_async_smem();
       mbar_arrive(bar_go);
+    }
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / p.n_out;
+      const bool has_next = item + (int)gridDim.x < n_items;
+      long long* ds = (p.dbg != nullptr && blockIdx.x == 0 && tid == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 16 * (item / gridDim.x) : nullptr;
+      stamp(ds, 0);
+      if (!kStageAhead) {
+        stage_window(item, ds);
+        fence_async_smem();
+        mbar_arrive(bar_go);
+      }
       stamp(ds, 1);
 
       // ---- E1: bias + LayerNorm of token row tid -> enc (bf16, K-major) -------------------------------
@@ -585,6 +647,10 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       fence_async_smem();
       mbar_arrive(bar_go);
       stamp(ds, 3);
+      if (kStageAhead) {
+        // the S/VT GEMMs (weight-streaming bound, ~8 k cycles) need nothing from these warps: stage the next window now
+        if (has_next) stage_window(item + gridDim.x, ds);
+      }
 
       // ---- E2 softmax rows -> P tiles;  E3 vT rows (+ bv) -> vT tiles ---------------------------------
       mbar_wait(bar_done, done_phase), done_phase ^= 1;
@@ -619,7 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         const float inv = lane < KOE_N_MOUTH ? 1.0f / sum : 0.0f;
 #pragma unroll
         for (int i = 0; i < kTok; ++i) s[i] *= inv;
-        unsigned char* prow = smem + kOffX + t * kPTile + (row >> 3) * kPSbo + (row & 7) * 16;
+        unsigned char* prow = smem + kOffE + t * kPTile + (row >> 3) * kPSbo + (row & 7) * 16;
 #pragma unroll
         for (int c = 0; c < 10; ++c) *reinterpret_cast<uint4*>(prow + c * 128) = pack8_bf16(s + 8 * c);
         if (p.attn_out != nullptr && lane < KOE_N_MOUTH) {
@@ -680,6 +746,10 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       mbar_wait(bar_done, done_phase), done_phase ^= 1;
       stamp(ds, 8);
       tc_fence_after();
+      if (kStageAhead && has_next) {  // the next window's first GEMM (TMEM columns [0, 256)) runs under the decoder tail
+        fence_async_smem();
+        mbar_arrive(bar_go);
+      }
       if (warp == 0) {
         float logit = 0.0f;
         for (int c0 = 0; c0 < 128; c0 += 32) {

@@ -66,6 +66,7 @@ struct LogmelParams {
   float* power;
   float* frame_max;
   long long power_clip_stride, fmax_clip_stride;  // elements between consecutive clips' output blocks
+  int edge_lo, edge_hi;          // leading / trailing frame pairs of a clip that need masked loads (launch order only)
 };
 
 __host__ __device__ constexpr int bitrev5(int i) {
@@ -130,6 +131,9 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
 }
 
 // Where a frame pair lives: clip, first frame (< 0: no pair), first sample of both frames, valid sample ranges.
+__host__ __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+
 struct PairInfo {
   int clip, frame;
   int fa_lo, fb_lo;            // first sample of frame A / frame B (may be negative)
@@ -137,31 +141,9 @@ struct PairInfo {
   bool interior, has_b;
 };
 
-__device__ __forceinline__ PairInfo locate_pair(const LogmelParams& p, unsigned pair, unsigned total_pairs, unsigned ppc) {
+// geometry of frame pair j (frames 2j, 2j + 1) of clip b
+__host__ __device__ __forceinline__ PairInfo pair_geometry(const LogmelParams& p, int b, int j) {
   PairInfo pi;
-  pi.clip = 0;
-  pi.frame = -1;
-  pi.interior = false;
-  if (pair >= total_pairs) return pi;
-  // Launch order of the pairs: every clip's first pair, then every clip's last pair, then the middle ones clip by clip.
-  // The first / last pairs are the ones that touch the padding and take the masked loads (~25 % more instructions for
-  // that warp); grouped, they fill whole 16-warp iterations instead of holding 15 interior warps at the barrier in one
-  // iteration out of five.
-  int b, j;
-  if (ppc <= 2) {
-    b = (int)(pair / ppc);
-    j = (int)(pair - (unsigned)b * ppc);
-  } else if (pair < (unsigned)p.n_clips) {
-    b = (int)pair;
-    j = 0;
-  } else if (pair < 2u * (unsigned)p.n_clips) {
-    b = (int)pair - p.n_clips;
-    j = (int)ppc - 1;
-  } else {
-    const unsigned r = pair - 2u * (unsigned)p.n_clips;
-    b = (int)(r / (ppc - 2));
-    j = 1 + (int)(r - (unsigned)b * (ppc - 2));
-  }
   const int ga = 2 * j;
   pi.clip = b;
   pi.frame = ga;
@@ -169,12 +151,12 @@ __device__ __forceinline__ PairInfo locate_pair(const LogmelParams& p, unsigned 
   const int fa = p.frame_offset + ga * p.frame_step, fb = fa + p.frame_step;  // frame indices in hops
   pi.lo_a = 0, pi.hi_a = p.n_samples, pi.lo_b = 0, pi.hi_b = p.n_samples;
   if (p.lo_rel != KOE_NO_EDGE) {
-    pi.lo_a = max(pi.lo_a, p.sample_offset + (fa + p.lo_rel) * p.hop);
-    pi.lo_b = max(pi.lo_b, p.sample_offset + (fb + p.lo_rel) * p.hop);
+    pi.lo_a = imax(pi.lo_a, p.sample_offset + (fa + p.lo_rel) * p.hop);
+    pi.lo_b = imax(pi.lo_b, p.sample_offset + (fb + p.lo_rel) * p.hop);
   }
   if (p.hi_rel != KOE_NO_EDGE) {
-    pi.hi_a = min(pi.hi_a, p.sample_offset + (fa + p.hi_rel) * p.hop);
-    pi.hi_b = min(pi.hi_b, p.sample_offset + (fb + p.hi_rel) * p.hop);
+    pi.hi_a = imin(pi.hi_a, p.sample_offset + (fa + p.hi_rel) * p.hop);
+    pi.hi_b = imin(pi.hi_b, p.sample_offset + (fb + p.hi_rel) * p.hop);
   }
   if (!pi.has_b) pi.hi_b = pi.lo_b;  // empty range: second frame reads as silence
   pi.fa_lo = p.sample_offset + fa * p.hop - kFrameLen / 2;
@@ -182,6 +164,39 @@ __device__ __forceinline__ PairInfo locate_pair(const LogmelParams& p, unsigned 
   pi.interior = pi.fa_lo >= pi.lo_a && pi.fa_lo + kFrameLen <= pi.hi_a && pi.fb_lo >= pi.lo_b &&
                 pi.fb_lo + kFrameLen <= pi.hi_b;
   return pi;
+}
+
+// Launch order of the pairs: every clip's leading edge pairs, then every clip's trailing edge pairs, then the interior ones
+// clip by clip.  Edge pairs are the ones that touch the padding, a window edge or the end of the clip and take the masked
+// loads (~25 % more instructions for that warp); grouped, they fill whole 16-warp iterations instead of holding 15
+// interior warps at the barrier in every few iterations.  edge_lo / edge_hi are counted on the host (same geometry).
+__device__ __forceinline__ PairInfo locate_pair(const LogmelParams& p, unsigned pair, unsigned total_pairs, unsigned ppc) {
+  if (pair >= total_pairs) {
+    PairInfo pi;
+    pi.clip = 0;
+    pi.frame = -1;
+    pi.interior = false;
+    return pi;
+  }
+  const unsigned mid = ppc - (unsigned)(p.edge_lo + p.edge_hi);
+  const unsigned n_lo = (unsigned)p.n_clips * (unsigned)p.edge_lo, n_hi = (unsigned)p.n_clips * (unsigned)p.edge_hi;
+  int b, j;
+  if (p.edge_lo + p.edge_hi == 0 || (unsigned)(p.edge_lo + p.edge_hi) >= ppc) {
+    b = (int)(pair / ppc);
+    j = (int)(pair - (unsigned)b * ppc);
+  } else if (pair < n_lo) {
+    b = (int)(pair / (unsigned)p.edge_lo);
+    j = (int)(pair - (unsigned)b * (unsigned)p.edge_lo);
+  } else if (pair < n_lo + n_hi) {
+    const unsigned r = pair - n_lo;
+    b = (int)(r / (unsigned)p.edge_hi);
+    j = (int)(ppc - (unsigned)p.edge_hi + (r - (unsigned)b * (unsigned)p.edge_hi));
+  } else {
+    const unsigned r = pair - n_lo - n_hi;
+    b = (int)(r / mid);
+    j = p.edge_lo + (int)(r - (unsigned)b * mid);
+  }
+  return pair_geometry(p, b, j);
 }
 
 // interior frames (all but the first / last of a clip): no masking.  v[bitrev5(n1)] = (a[32 n1 + lane], b[32 n1 + lane])
@@ -834,6 +849,13 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
   p.frame_max = a->frame_max;
   p.power_clip_stride = a->power_clip_stride;
   p.fmax_clip_stride = a->frame_max_clip_stride;
+  {
+    const int ppc = (p.n_frames + 1) / 2;
+    p.edge_lo = 0;
+    while (p.edge_lo < ppc && !pair_geometry(p, 0, p.edge_lo).interior) ++p.edge_lo;
+    p.edge_hi = 0;
+    while (p.edge_lo + p.edge_hi < ppc && !pair_geometry(p, 0, ppc - 1 - p.edge_hi).interior) ++p.edge_hi;
+  }
   const long long ppc = (a->n_frames + 1) / 2;
   KOE_REQUIRE((long long)a->n_clips * ppc < (1ll << 31) - kWarps, "koe_logmel_power: more than 2^31 frame pairs in one call");
   const long long n_blocks = ((long long)a->n_clips * ppc + kWarps - 1) / kWarps;

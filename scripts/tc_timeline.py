@@ -25,7 +25,13 @@ names_m = ["go1", "G1 issued", "go2", "S/VT issued", "go3", "PV issued", "go4", 
 for wdw in range(2):
     print("window", wdw)
     ev = [(d[16 * wdw + i] - t0, "SIMT " + names_s[i]) for i in range(10)] + \
-         [(d[64 + 16 * wdw + i] - t0, "MMA  " + names_m[i]) for i in range(8)]
+         [(d[16 * wdw + 10 + i] - t0, "SIMT   staging: " + n) for i, n in enumerate(
+             ["dB reference done", "mel stage 0 staged", "mel stage 2 staged", "mel stages staged"]) if d[16 * wdw + 10 + i]] + \
+         [(d[64 + 16 * wdw + i] - t0, "MMA  " + names_m[i]) for i in range(8)] + \
+         [(d[64 + 16 * wdw + 8 + i] - t0, f"MMA    H1 stage {i} arrived") for i in range(4)] + \
+         [(d[64 + 16 * wdw + 12 + i] - t0, f"MMA    G1 stage {(0, 1, 2, 'last')[i]} arrived") for i in range(4)] + \
+         [(d[32 + 16 * wdw + i] - t0, "TMA      issue " + n) for i, n in enumerate(
+             ["H1 s0", "H1 s1", "H1 s2", "H1 s3", "G1 s0", "G1 last", "S/VT s0", "S/VT last", "mel s0", "mel last"])]
     prev = None
     for t, n in sorted(ev):
         print(f"  {t:8d} cyc  (+{0 if prev is None else t - prev:6d})  {n}")
