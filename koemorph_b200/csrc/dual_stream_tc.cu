@@ -428,16 +428,33 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
     const uint32_t lane_taddr = tmem + ((uint32_t)(32 * wq) << 16);
     const bool prenorm = p.mel_long != nullptr;
     // first-GEMM operand of one window: dB reference, normalise, bf16, K-major core matrices in the X region
-    auto stage_window = [&](const int item, long long* ds) {
+    // this thread's share of a window's per-frame maxima (its dB reference is their maximum): independent loads, issued
+    // together; for the stage-ahead path they are requested one phase early so that their latency is never waited for
+    auto frame_max_partial = [&](const int item) {
+      float mx = -INFINITY;
+      if (!prenorm) {
+        const int b = item / p.n_out, wi = item % p.n_out;
+        for (int k0 = tid; k0 < T; k0 += 3 * kSimt) {
+          float f[3];
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            const int k = k0 + u * kSimt;
+            f[u] = -INFINITY;
+            if (k < T) {
+              const int v = window_variant(p, k);
+              f[u] = p.fmax[v][window_row(p, v, b, wi, k)];
+            }
+          }
+          mx = fmaxf(fmaxf(mx, f[0]), fmaxf(f[1], f[2]));
+        }
+      }
+      return mx;
+    };
+    auto stage_window = [&](const int item, float mx, long long* ds) {
       const int b = item / p.n_out, wi = item % p.n_out;
       // ---- window dB reference
       float ref_db = 0.0f;
       if (!prenorm) {
-        float mx = -INFINITY;
-        for (int k = tid; k < T; k += kSimt) {
-          const int v = window_variant(p, k);
-          mx = fmaxf(mx, p.fmax[v][window_row(p, v, b, wi, k)]);
-        }
         mx = warp_max(mx);
         if (lane == 0) s_red[warp] = mx;
         simt_barrier();
@@ -449,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       if (tma_mel) {
         // ---- A1 from the TMA-staged rows: Xn[channel j][time t] as bf16, one 16-byte store = 8 frames of a channel
         // rows that are not plain frames of this window (short-term detail, edge variants) are fetched directly, early
-        float extra[4] = {0.f, 0.f, 0.f, 0.f};            // [0..2] short-term frames T-3+s, [3] lo-edge frame 0
+        float extra[5] = {0.f, 0.f, 0.f, 0.f, 0.f};       // [0..2] short-term frames T-3+s, [3] lo-edge frame 0, [4] hi-edge frame T-1
         if (tid < kTok) {
 #pragma unroll
           for (int e = 0; e < 3; ++e) {
@@ -461,21 +478,46 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
               extra[e] = -INFINITY;
             }
           }
-          if (p.n_edge > 0) extra[3] = __ldg(p.power[1] + window_row(p, 1, b, wi, 0) * kTok + tid);
+          if (p.n_edge > 0) {
+            extra[3] = __ldg(p.power[1] + window_row(p, 1, b, wi, 0) * kTok + tid);
+            if (T - 1 < Tl) extra[4] = __ldg(p.power[2] + window_row(p, 2, b, wi, T - 1) * kTok + tid);
+          }
         }
         for (int s = 0; s < n_mel_stages; ++s) {
           mbar_wait(bar_full + 8 * slot, phase);
           const float* raw = reinterpret_cast<const float*>(smem + kOffRing + slot * kStageBytes);
           const int rows = min(kMelRows, Tl - kMelRows * s);
           const int chunks = (rows + 7) >> 3;
-          for (int idx = tid; idx < chunks * kTok; idx += kSimt) {
-            const int c = idx / kTok, j = idx % kTok;
-            float v[8];
+          if (rows == kMelRows) {
+            // full stage: 6 chunks x 80 channels = 480 items of 8 frames; a thread's two items are loaded together
+            static_assert(kMelRows * kTok / 8 <= 2 * kSimt, "two items per thread cover a stage");
+            const int i0 = tid, i1 = tid + kSimt;
+            const bool two = i1 < kMelRows * kTok / 8;
+            const int c0 = i0 / kTok, j0 = i0 % kTok, c1 = two ? i1 / kTok : c0, j1 = two ? i1 % kTok : j0;
+            float v0[8], v1[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              v[e] = 8 * c + e < rows ? normalise_bf16(raw[(8 * c + e) * kTok + j], ref_db, true) : 0.0f;
-            *reinterpret_cast<uint4*>(smem + kOffX + (j >> 3) * kA1Sbo + (6 * s + c) * 128 + (j & 7) * 16) =
-                pack8_bf16(v);
+            for (int e = 0; e < 8; ++e) {
+              v0[e] = raw[(8 * c0 + e) * kTok + j0];
+              v1[e] = raw[(8 * c1 + e) * kTok + j1];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              v0[e] = normalise_bf16(v0[e], ref_db, true);
+              v1[e] = normalise_bf16(v1[e], ref_db, true);
+            }
+            *reinterpret_cast<uint4*>(smem + kOffX + (j0 >> 3) * kA1Sbo + (6 * s + c0) * 128 + (j0 & 7) * 16) = pack8_bf16(v0);
+            if (two)
+              *reinterpret_cast<uint4*>(smem + kOffX + (j1 >> 3) * kA1Sbo + (6 * s + c1) * 128 + (j1 & 7) * 16) = pack8_bf16(v1);
+          } else {
+            for (int idx = tid; idx < chunks * kTok; idx += kSimt) {
+              const int c = idx / kTok, j = idx % kTok;
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                v[e] = 8 * c + e < rows ? normalise_bf16(raw[(8 * c + e) * kTok + j], ref_db, true) : 0.0f;
+              *reinterpret_cast<uint4*>(smem + kOffX + (j >> 3) * kA1Sbo + (6 * s + c) * 128 + (j & 7) * 16) =
+                  pack8_bf16(v);
+            }
           }
           simt_barrier();                                   // every thread is done reading this ring slot
           if (s == 0) stamp(ds, 11);
@@ -503,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
                 __float2bfloat16_rn(normalise_bf16(lo, ref_db, true));
             const int k = T - 1 - m;
             if (k < Tl) {
-              const float x = __ldg(p.power[2 + 2 * m] + window_row(p, 2 + 2 * m, b, wi, k) * kTok + j);
+              const float x = m == 0 ? extra[4] : __ldg(p.power[2 + 2 * m] + window_row(p, 2 + 2 * m, b, wi, k) * kTok + j);
               *reinterpret_cast<__nv_bfloat16*>(arow + (k >> 3) * 128 + (k & 7) * 2) =
                   __float2bfloat16_rn(normalise_bf16(x, ref_db, true));
             }
@@ -584,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       }
     };
     if (kStageAhead && (int)blockIdx.x < n_items) {
-      stage_window(blockIdx.x, nullptr);
+      stage_window(blockIdx.x, frame_max_partial(blockIdx.x), nullptr);
       fence_async_smem();
       mbar_arrive(bar_go);
     }
@@ -594,11 +636,12 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       long long* ds = (p.dbg != nullptr && blockIdx.x == 0 && tid == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 16 * (item / gridDim.x) : nullptr;
       stamp(ds, 0);
       if (!kStageAhead) {
-        stage_window(item, ds);
+        stage_window(item, frame_max_partial(item), ds);
         fence_async_smem();
         mbar_arrive(bar_go);
       }
       stamp(ds, 1);
+      const float mx_next = kStageAhead && has_next ? frame_max_partial(item + gridDim.x) : -INFINITY;
 
       // ---- E1: bias + LayerNorm of token row tid -> enc (bf16, K-major) -------------------------------
       mbar_wait(bar_done, done_phase), done_phase ^= 1;
@@ -649,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       stamp(ds, 3);
       if (kStageAhead) {
         // the S/VT GEMMs (weight-streaming bound, ~8 k cycles) need nothing from these warps: stage the next window now
-        if (has_next) stage_window(item + gridDim.x, ds);
+        if (has_next) stage_window(item + gridDim.x, mx_next, ds);
       }
 
       // ---- E2 softmax rows -> P tiles;  E3 vT rows (+ bv) -> vT tiles ---------------------------------
