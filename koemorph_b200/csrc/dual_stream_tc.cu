@@ -218,8 +218,11 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   // barriers: full[kRing], empty[kRing], mma_go, mma_done
   const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kRing;
   const uint32_t bar_go = bar_empty + 8 * kRing, bar_done = bar_go + 8;
-  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 2));
-  float* s_red = reinterpret_cast<float*>(smem + kOffBar + 8 * (2 * kRing + 2) + 16);  // [8]
+  // the VT tiles' completion has its own barrier: the SIMT warps may still be staging the next window when both the VT
+  // and the S tiles complete, and a waiter two phases behind on one barrier would never see its parity
+  const uint32_t bar_vt = bar_done + 8;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 3));
+  float* s_red = reinterpret_cast<float*>(smem + kOffBar + 8 * (2 * kRing + 3) + 16);  // [8]
   float* s_const = reinterpret_cast<float*>(smem + kOffConst);
   const float* s_bv = s_const + 768;
   const float *s_ba = s_const + 1024, *s_w2 = s_const + 1152;
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
     }
     mbar_init(bar_go, kSimt);
     mbar_init(bar_done, 1);
+    mbar_init(bar_vt, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < kSimt) {
@@ -280,7 +284,10 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           if (s == kStagesG1) stamp(dp, 6);
           if (s == kStagesPerWindow - 5) stamp(dp, 7);
           mbar_expect_tx(bar_full + 8 * slot, kStageBytes);
-          bulk_g2s_hint(sbase + kOffRing + slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
+          // the pre-tiled buffer holds [G1 | S tile 0, 1 | VT tile 0, 1 | H1]; the VT tiles are streamed before the S tiles
+          // so that their epilogue runs while the S tiles are still on the tensor core
+          const int ss = s < kStagesG1 || s >= kStagesG1 + 16 ? s : (s < kStagesG1 + 8 ? s + 8 : s - 8);
+          bulk_g2s_hint(sbase + kOffRing + slot * kStageBytes, src + (size_t)ss * kStageBytes, kStageBytes,
                         bar_full + 8 * slot, pol_keep);
           if (++slot == kWRing) slot = 0, phase ^= 1;
         }
@@ -356,13 +363,13 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           advance();
         }
         stamp(dm, 1);
-        // ---- S (2 tiles) and VT (2 tiles): A = weight stage [128 x 64], B = enc [80 x 256]
+        // ---- VT (2 tiles), then S (2 tiles): A = weight stage [128 x 64], B = enc [80 x 256]
         mbar_wait(bar_go, go_phase), go_phase ^= 1;
         stamp(dm, 2);
         tc_fence_after();
         for (int js = 0; js < 4 * kStagesTile; ++js) {
-          const int tile = js >> 2, s = js & 3;
-          const uint32_t d = tmem + (tile < 2 ? kColS + 80 * tile : kColVT + 80 * (tile - 2));
+          const int tile = js >> 2, s = js & 3;  // tiles 0, 1: VT; 2, 3: S
+          const uint32_t d = tmem + (tile < 2 ? kColVT + 80 * tile : kColS + 80 * (tile - 2));
           mbar_wait(bar_full + 8 * slot, phase);
           tc_fence_after();
           if (elect_one()) {
@@ -372,6 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
             for (int j = 0; j < 4; ++j)
               tc_mma_bf16(d, a + j * (256 >> 4), b + j * (256 >> 4), idesc_bf16(128, 80), (s | j) != 0);
             tc_commit(bar_empty + 8 * slot);
+            if (js == 2 * kStagesTile - 1) tc_commit(bar_vt);
             if (js == 4 * kStagesTile - 1) tc_commit(bar_done);
           }
           __syncwarp();
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
     // =========================================================== SIMT warps 0-7 ========================
     // warpgroup wg = warp / 4; warps w and w + 4 both own TMEM lanes 32 (w % 4) .. +31, so the two warpgroups split
     // every epilogue between them (LayerNorm: column halves; softmax / vT / O: one tile of 4 heads each)
-    uint32_t done_phase = 0, slot = kWRing, phase = 0;  // (slot, phase): the mel-row ring
+    uint32_t done_phase = 0, vt_phase = 0, slot = kWRing, phase = 0;  // (slot, phase): the mel-row ring
     const int wg = warp >> 2, wq = warp & 3;
     const int row = 32 * wq + lane;                                        // TMEM lane == accumulator row
     const uint32_t lane_taddr = tmem + ((uint32_t)(32 * wq) << 16);
@@ -695,7 +703,33 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         if (has_next) stage_window(item + gridDim.x, mx_next, ds);
       }
 
-      // ---- E2 softmax rows -> P tiles;  E3 vT rows (+ bv) -> vT tiles ---------------------------------
+      // ---- E3 vT rows (+ bv) -> vT tiles, as soon as the VT tiles are done (the S tiles are still streaming) ----------
+      mbar_wait(bar_vt, vt_phase), vt_phase ^= 1;
+      tc_fence_after();
+      {
+        const int t = wg;
+        float s[kTok];
+        {
+          float v[32];
+          tmem_ld32(lane_taddr + kColVT + 80 * t, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] = v[i];
+          tmem_ld32(lane_taddr + kColVT + 80 * t + 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[32 + i] = v[i];
+          float u[16];
+          tmem_ld16(lane_taddr + kColVT + 80 * t + 64, u);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s[64 + i] = u[i];
+        }
+        const float bias = s_bv[128 * t + row];
+#pragma unroll
+        for (int i = 0; i < kTok; ++i) s[i] += bias;
+        unsigned char* vrow = smem + kOffVT + t * kPTile + (row >> 3) * kPSbo + (row & 7) * 16;
+#pragma unroll
+        for (int c = 0; c < 10; ++c) *reinterpret_cast<uint4*>(vrow + c * 128) = pack8_bf16(s + 8 * c);
+      }
+      // ---- E2 softmax rows -> P tiles (over enc, which the S GEMMs have now finished reading) -------------------
       mbar_wait(bar_done, done_phase), done_phase ^= 1;
       stamp(ds, 4);
       tc_fence_after();
@@ -736,29 +770,6 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
 #pragma unroll
           for (int i = 0; i < kTok; ++i) atomicAdd(dst + i, s[i] * (1.0f / KOE_N_HEADS));
         }
-      }
-      {
-        const int t = wg;
-        float s[kTok];
-        {
-          float v[32];
-          tmem_ld32(lane_taddr + kColVT + 80 * t, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[i] = v[i];
-          tmem_ld32(lane_taddr + kColVT + 80 * t + 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[32 + i] = v[i];
-          float u[16];
-          tmem_ld16(lane_taddr + kColVT + 80 * t + 64, u);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) s[64 + i] = u[i];
-        }
-        const float bias = s_bv[128 * t + row];
-#pragma unroll
-        for (int i = 0; i < kTok; ++i) s[i] += bias;
-        unsigned char* vrow = smem + kOffVT + t * kPTile + (row >> 3) * kPSbo + (row & 7) * 16;
-#pragma unroll
-        for (int c = 0; c < 10; ++c) *reinterpret_cast<uint4*>(vrow + c * 128) = pack8_bf16(s + 8 * c);
       }
       tc_fence_before();
       fence_async_smem();
