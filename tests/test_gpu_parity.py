@@ -339,3 +339,37 @@ def test_pcm16_conversion_is_exact_and_host_pipeline_accepts_it(K):
     assert torch.equal(want, ref)
     with pytest.raises(ValueError):
         pipe(torch.zeros(2, 136000, dtype=torch.float64), torch.from_numpy(eg[:2]))
+
+
+@pytest.mark.parametrize("L,hop,n_frames,frame_offset,pad_mode", [
+    (136000, 533, 257, 0, "constant"),   # bench shape: frame 255 and 256 run past the clip (three edge pairs)
+    (136000, 533, 256, 0, "constant"),
+    (20000, 533, 38, 0, "constant"),     # short clip: 1 + L // hop frames
+    (20000, 533, 5, 3, "constant"),      # a few interior frames only (no edge pair at either end)
+    (3000, 533, 6, 0, "constant"),       # shorter than two frames: every pair touches an edge
+    (700, 533, 2, 0, "constant"),        # shorter than one frame
+    (1500, 533, 1, 1, "constant"),       # a single frame = a single half-empty pair
+    (20000, 266, 76, 0, "constant"),     # 60 fps hop: two leading / trailing edge frames
+    (20000, 533, 38, 0, "reflect"),      # MelSlidingWindowExtractor padding
+])
+def test_logmel_launch_order_over_ragged_shapes(K, L, hop, n_frames, frame_offset, pad_mode):
+    """The frontend launches a clip's padding-touching frame pairs ahead of its interior ones (they take masked loads);
+    whatever the split -- no edge pairs, only edge pairs, odd frame counts, several clips -- every output row must still be
+    the frame it is documented to be: compared with the float64 restatement of librosa's STFT + mel."""
+    from koemorph_b200.features.mel_frontend import LogMelFrontend
+    B = 5
+    audio, _ = O.make_inputs(1000 + L + n_frames, B, L, "speechlike")
+    fe = LogMelFrontend.get("cuda")
+    db, fmax = fe.power(torch.from_numpy(audio).cuda(), hop, n_frames, frame_offset=frame_offset, pad_mode=pad_mode)
+    db = db.cpu().double().numpy()
+    assert db.shape == (B, n_frames, 80)
+    for b in range(B):
+        full = O.melspectrogram(audio[b], hop_length=hop, pad_mode=pad_mode, exact=True).T   # (1 + L // hop, 80)
+        have = min(n_frames, max(0, full.shape[0] - frame_offset))
+        ref = full[frame_offset:frame_offset + have]
+        got = 10 ** (db[b, :have] / 10)
+        assert np.abs(got - np.maximum(ref, 1e-10)).max() <= 2e-6 * max(full.max(), 1e-10)
+        big = ref > 1e-6 * full.max()
+        if big.any():
+            assert np.abs(db[b, :have] - 10 * np.log10(np.maximum(ref, 1e-10)))[big].max() < 8.7e-4
+        np.testing.assert_allclose(fmax[b].cpu().numpy(), db[b].max(axis=1), rtol=1e-6)
