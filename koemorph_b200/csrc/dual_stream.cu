@@ -394,13 +394,33 @@ __global__ void __launch_bounds__(256) emotion_stream_kernel(koe_core_weights W,
     __syncthreads();
     const float* wb = s_buf + (chunk & 1) * kEmoBufFloats + tid;
     const int r0 = chunk * kEmoChunkRows, rows = min(kEmoChunkRows, W.emo_in - r0);
-#pragma unroll 4
-    for (int k = 0; k < rows; ++k) {
-      const float w = wb[k * kD];
-      const float4* xr = reinterpret_cast<const float4*>(s_x + (r0 + k) * kEmoClips);
+    // eight rows per step: the 8 weight loads and 8 broadcast input loads are issued together (two warps per scheduler
+    // cannot hide a shared-memory round trip per row: `short_scoreboard` was 37 % of the samples)
+    const float4* xr0 = reinterpret_cast<const float4*>(s_x + r0 * kEmoClips);
+    int k = 0;
+    for (; k + 8 <= rows; k += 8) {
+      float w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = wb[(k + u) * kD];
 #pragma unroll
       for (int q = 0; q < kEmoClips / 4; ++q) {
-        const float4 x = xr[q];
+        float4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = xr0[(k + u) * (kEmoClips / 4) + q];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          z[4 * q + 0] = fmaf(w[u], x[u].x, z[4 * q + 0]);
+          z[4 * q + 1] = fmaf(w[u], x[u].y, z[4 * q + 1]);
+          z[4 * q + 2] = fmaf(w[u], x[u].z, z[4 * q + 2]);
+          z[4 * q + 3] = fmaf(w[u], x[u].w, z[4 * q + 3]);
+        }
+      }
+    }
+    for (; k < rows; ++k) {
+      const float w = wb[k * kD];
+#pragma unroll
+      for (int q = 0; q < kEmoClips / 4; ++q) {
+        const float4 x = xr0[k * (kEmoClips / 4) + q];
         z[4 * q + 0] = fmaf(w, x.x, z[4 * q + 0]);
         z[4 * q + 1] = fmaf(w, x.y, z[4 * q + 1]);
         z[4 * q + 2] = fmaf(w, x.z, z[4 * q + 2]);
@@ -455,7 +475,7 @@ __global__ void __launch_bounds__(256) emotion_stream_kernel(koe_core_weights W,
     __syncthreads();   // also orders the s_z writes above before the first read
     const float* wb = s_buf + (chunk & 1) * kEmoBufFloats + j;
     const int r0 = (chunk - n1) * kEmoChunkRows;
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < kEmoChunkRows; ++k) {
       const float w = wb[k * 128];
       const float* zr = s_z + (r0 + k) * kEmoClips + half * (kEmoClips / 2);
