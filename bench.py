@@ -216,10 +216,12 @@ def run_gpu(args):
             k1_events.append((e0, e1))
         else:
             power, fmax = fe.power(audio, model.hop_length, n_frames)
-        out, _, _ = model._core_windows([power], [fmax], 0, B, n_frames, 1, 1, n_frames, eg, False)
+        # multi-GPU: the step's frames land directly in their slot of the buffer that is gathered at the end
+        slot = None
         if kept is not None:
-            kept[step_no[0] % kept.shape[0]].copy_(out)   # results stay on the device until the gather
+            slot = kept[step_no[0] % kept.shape[0]]
             step_no[0] += 1
+        out, _, _ = model._core_windows([power], [fmax], 0, B, n_frames, 1, 1, n_frames, eg, False, out=slot)
         return out
 
     def gather_all():
@@ -237,6 +239,8 @@ def run_gpu(args):
     ref = model(audio[:8].contiguous(), egemaps=eg[:8].contiguous())["blendshapes"]
     for _ in range(max(args.warmup, 3)):
         out = step(False)
+    gather_all()  # warm-up covers the collective too (first use sets up NCCL's channels for this size)
+    step_no[0] = 0
     barrier()
     assert torch.equal(out[:8], ref), "bench step diverges from SequentialDualStreamModel.forward"
 

@@ -629,7 +629,10 @@ extern "C" int koe_emotion_stream(const koe_core_weights* w, const float* emo_in
 }
 
 static long long* g_tc_debug = nullptr;
-extern "C" void koe_debug_set_tc_timestamps(long long* device_buffer_128) { g_tc_debug = device_buffer_128; }
+// bring-up / profiling hook (not in the public header; scripts/tc_timeline.py): a device buffer of 128 + 2 * gridDim
+// 64-bit slots that the tensor-core kernel fills with phase timestamps of CTA 0 (clock64) and every CTA's start / end
+// (globaltimer); NULL (the default) turns the stamps off
+extern "C" void koe_debug_set_tc_timestamps(long long* device_buffer) { g_tc_debug = device_buffer; }
 
 static int launch_core(const CoreParams& p_in, int precision, cudaStream_t stream) {
   CoreParams p = p_in;

@@ -214,6 +214,13 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const koe_core_weights& W = p.w;
+  long long* dk = (p.dbg != nullptr && blockIdx.x == 0 && tid == 0) ? p.dbg + 120 : nullptr;
+  stamp(dk, 0);
+  if (p.dbg != nullptr && tid == 0) {  // per-CTA wall-clock span (ns) for the launch-level picture
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[128 + 2 * blockIdx.x] = (long long)g;
+  }
 
   // barriers: full[kRing], empty[kRing], mma_go, mma_done
   const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kRing;
@@ -260,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
+  stamp(dk, 1);
 
   const int n_items = p.n_clips * p.n_out;
   const int T = p.frames_per_window;
@@ -637,6 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       stage_window(blockIdx.x, frame_max_partial(blockIdx.x), nullptr);
       fence_async_smem();
       mbar_arrive(bar_go);
+      stamp(dk, 2);
     }
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.n_out;
@@ -830,12 +839,18 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       tc_fence_before();
       simt_barrier();  // the next window's A1 staging overwrites the P tiles only after every row is consumed
     }
+    stamp(dk, 3);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  }
+  if (p.dbg != nullptr && tid == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[129 + 2 * blockIdx.x] = (long long)g;
   }
 }
 

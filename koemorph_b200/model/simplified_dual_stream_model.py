@@ -161,13 +161,17 @@ class SimplifiedDualStreamModel(nn.Module):
         return x
 
     def _core_windows(self, power_list, fmax_list, n_edge, B, n_frames, n_out, stride, frames_per_window, eg,
-                      return_attention):
-        """koe_emotion_stream + koe_dual_stream_windows on prepared mel-power buffers."""
+                      return_attention, out=None):
+        """koe_emotion_stream + koe_dual_stream_windows on prepared mel-power buffers; ``out`` may be a preallocated
+        contiguous (B, n_out, 52) float32 tensor (a corpus sweep writes every chunk's frames where they will be gathered)."""
         lib = _lib.load()
         dev = eg.device
         w = self.dual_stream_attention.kernel_weights(self._compression)
         expr = torch.empty(B, dtype=torch.float32, device=dev)
-        out = torch.empty(B, n_out, 52, dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty(B, n_out, 52, dtype=torch.float32, device=dev)
+        elif out.shape != (B, n_out, 52) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+            raise ValueError(f"out must be a contiguous float32 ({B}, {n_out}, 52) tensor on {dev}")
         sig = torch.empty(B, n_out, 52, dtype=torch.float32, device=dev) if return_attention else None
         attn = torch.empty(B, n_out, 28, 80, dtype=torch.float32, device=dev) if return_attention else None
         n_buf = 1 + 2 * _lib.MAX_EDGE

@@ -12,7 +12,7 @@ m.precision = "bf16"
 B = 512
 a = 0.1 * torch.randn(B, 136000, device="cuda"); e = torch.randn(B, 264, device="cuda")
 for _ in range(3): m(a, egemaps=e)
-dbg = torch.zeros(128, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(128 + 2 * 148, dtype=torch.int64, device="cuda")
 lib = _lib.load()
 lib.koe_debug_set_tc_timestamps.argtypes = [C.c_void_p]
 lib.koe_debug_set_tc_timestamps(dbg.data_ptr())
@@ -20,6 +20,13 @@ m(a, egemaps=e); torch.cuda.synchronize()
 lib.koe_debug_set_tc_timestamps(None)
 d = dbg.cpu().tolist()
 t0 = d[0]
+print('CTA 0: kernel entry %d, prologue done %d, first window staged %d, last window done %d (cycles, relative to window 0 SIMT start)' % tuple(d[120 + i] - d[0] for i in range(4)))
+import numpy as np
+span = np.array(d[128:128 + 296]).reshape(148, 2)
+t_first = span[:, 0].min()
+print('per-CTA wall clock (us after the first CTA started): start min/median/max %.1f %.1f %.1f, end min/median/max %.1f %.1f %.1f' % (
+    *(np.percentile(span[:, 0] - t_first, [0, 50, 100]) / 1e3), *(np.percentile(span[:, 1] - t_first, [0, 50, 100]) / 1e3)))
+print('  CTAs with 4 windows (blockIdx < 68): end median %.1f us; with 3 windows: %.1f us' % (np.median(span[:68, 1] - t_first) / 1e3, np.median(span[68:, 1] - t_first) / 1e3))
 names_s = ["start", "staged", "G1 done", "E1 done", "S/VT done", "E2/3 done", "PV done", "E4 done", "H1 done", "E5 done"]
 names_m = ["go1", "G1 issued", "go2", "S/VT issued", "go3", "PV issued", "go4", "H1 issued"]
 for wdw in range(2):
@@ -36,3 +43,16 @@ for wdw in range(2):
     for t, n in sorted(ev):
         print(f"  {t:8d} cyc  (+{0 if prev is None else t - prev:6d})  {n}")
         prev = t
+
+# whole-launch time of the core kernel alone for the same batch (events around 10 launches), for scale
+import ctypes
+power, fmax = m._frontend(a.device).power(a, m.hop_length, 257)
+eg = m._check_egemaps(e, B, a.device)
+for _ in range(3):
+    m._core_windows([power], [fmax], 0, B, 257, 1, 1, 257, eg, False)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    m._core_windows([power], [fmax], 0, B, 257, 1, 1, 257, eg, False)
+e1.record(); torch.cuda.synchronize()
+print("emotion + core kernels, 512 windows: %.1f us per call (clock %d MHz nominal 1965)" % (e0.elapsed_time(e1) * 100, 1965))
