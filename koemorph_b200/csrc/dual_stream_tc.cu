@@ -669,19 +669,19 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         const bool live = 32 * wq < kTok;
         const int cb = 128 * wg;                       // this warpgroup's half of the 256 features
         if (live) {
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};  // four chains each (latency)
+#pragma unroll
           for (int c0 = 0; c0 < 128; c0 += 32) {
             float v[32];
             tmem_ld32(lane_taddr + kColD1 + cb + c0, v);
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float x0 = v[i], x1 = v[i + 1];  // (the encoder bias came in through the GEMM)
-              s0 += x0, s1 += x1;
-              q0 = fmaf(x0, x0, q0), q1 = fmaf(x1, x1, q1);
+            for (int i = 0; i < 32; ++i) {  // (the encoder bias came in through the GEMM)
+              sa[i & 3] += v[i];
+              qa[i & 3] = fmaf(v[i], v[i], qa[i & 3]);
             }
           }
-          s_ln[wg * 128 + row] = s0 + s1;
-          s_ln[256 + wg * 128 + row] = q0 + q1;
+          s_ln[wg * 128 + row] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+          s_ln[256 + wg * 128 + row] = (qa[0] + qa[1]) + (qa[2] + qa[3]);
         }
         simt_barrier();
         if (live) {
@@ -759,15 +759,19 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
 #pragma unroll
           for (int i = 0; i < 16; ++i) s[64 + i] = u[i];
         }
-        float m = s[0];
+        // four interleaved chains for the maximum and the sum: with two warps per scheduler an 80-long dependent chain is
+        // pure latency
+        float m4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-        for (int i = 1; i < kTok; ++i) m = fmaxf(m, s[i]);
-        float sum = 0.0f;
+        for (int i = 4; i < kTok; ++i) m4[i & 3] = fmaxf(m4[i & 3], s[i]);
+        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int i = 0; i < kTok; ++i) {
           s[i] = __expf(s[i] - m);  // (the probabilities are rounded to bf16 next: MUFU.EX2 precision is ample)
-          sum += s[i];
+          sum4[i & 3] += s[i];
         }
+        const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         const float inv = lane < KOE_N_MOUTH ? 1.0f / sum : 0.0f;
 #pragma unroll
         for (int i = 0; i < kTok; ++i) s[i] *= inv;
