@@ -37,12 +37,36 @@ inline void count_launch(int n = 1) { launch_counter().fetch_add(n, std::memory_
                        __LINE__);                                                                 \
   } while (0)
 
+// launch with programmatic stream serialisation (see pdl_wait below)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_after_primary_starts(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                               cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 #define KOE_REQUIRE(cond, ...)                                   \
   do {                                                           \
     if (!(cond)) return koe::fail(KOE_E_INVALID, __VA_ARGS__);   \
   } while (0)
 
 // ---- device helpers ----------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_after_primary_starts() may begin while the
+// previous kernel of the stream is still running, as soon as every CTA of that kernel has executed
+// pdl_launch_dependents() (or exited) and an SM has room; it must execute pdl_wait() before it touches anything the
+// previous kernel writes -- pdl_wait() returns once the previous kernel has completed and its writes are visible.
+// Without the launch attribute both instructions are no-ops, so every kernel stays correct under a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 constexpr unsigned kFullMask = 0xffffffffu;
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(256) emotion_stream_kernel(koe_core_weights W,
   float* s_red = s_z + kD * kEmoClips;                  // [16][8]
   float* s_stat = s_red + 16 * 8;                       // [16][2]
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  pdl_launch_dependents();  // the core kernel may set itself up (barriers, TMEM, constants) while this one runs
   const int c0 = blockIdx.x * kEmoClips;
   const int nc = min(kEmoClips, n_clips - c0);
   const int n1 = (W.emo_in + kEmoChunkRows - 1) / kEmoChunkRows;   // chunks of we1_t [emo_in][256]
@@ -511,6 +512,9 @@ __global__ void __launch_bounds__(256) emotion_stream_kernel(koe_core_weights W,
     const float logit = s_red[tid * 8] + s_red[tid * 8 + 1] + s_red[tid * 8 + 2] + s_red[tid * 8 + 3] + W.b2;
     expr_sigmoid[c0 + tid] = 1.0f / (1.0f + expf(-logit));
   }
+  // this kernel reads nothing the frontend writes, so it may run beside the frontend's last CTAs; it still must not
+  // complete before the frontend has: the core kernel waits on THIS kernel only
+  pdl_wait();
 }
 
 // ---- EMA scan: y_t = alpha x_t + (1 - alpha) y_{t-1}, warp-parallel over 32 frames per step --------
@@ -620,9 +624,11 @@ extern "C" int koe_emotion_stream(const koe_core_weights* w, const float* emo_in
   }
   // every CTA streams all the weights (0.4 MB, L2 resident): few clips per CTA while that keeps the grid within ~4 waves
   if (n_clips <= 4 * 600)
-    emotion_stream_kernel<4><<<(n_clips + 3) / 4, 256, kEmoSmem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
+    KOE_CUDA(launch_after_primary_starts(emotion_stream_kernel<4>, dim3((n_clips + 3) / 4), dim3(256), kEmoSmem,
+                                         (cudaStream_t)stream, *w, emo_in, n_clips, expr_sigmoid));
   else
-    emotion_stream_kernel<16><<<(n_clips + 15) / 16, 256, kEmoSmem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
+    KOE_CUDA(launch_after_primary_starts(emotion_stream_kernel<16>, dim3((n_clips + 15) / 16), dim3(256), kEmoSmem,
+                                         (cudaStream_t)stream, *w, emo_in, n_clips, expr_sigmoid));
   count_launch();
   KOE_CUDA(cudaGetLastError());
   return KOE_OK;

@@ -268,6 +268,9 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
   stamp(dk, 1);
+  // everything above touched only this CTA's shared memory, TMEM and the weights; the mel rows, frame maxima and
+  // emotion-stream outputs read below come from the previous kernels of the stream
+  pdl_wait();
 
   const int n_items = p.n_clips * p.n_out;
   const int T = p.frames_per_window;
@@ -887,9 +890,9 @@ int launch_dual_stream_tc(const CoreParams& p, int precision, cudaStream_t strea
                              stream));
   const int grid = std::min(p.n_clips * p.n_out, num_sms[dev]);
   if (p.w.k_mel == 259)
-    tc::dual_stream_tc_kernel<259><<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(p);
+    KOE_CUDA(launch_after_primary_starts(tc::dual_stream_tc_kernel<259>, dim3(grid), dim3(tc::kThreads), tc::kSmemBytes, stream, p));
   else
-    tc::dual_stream_tc_kernel<515><<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(p);
+    KOE_CUDA(launch_after_primary_starts(tc::dual_stream_tc_kernel<515>, dim3(grid), dim3(tc::kThreads), tc::kSmemBytes, stream, p));
   count_launch();
   KOE_CUDA(cudaGetLastError());
   return KOE_OK;

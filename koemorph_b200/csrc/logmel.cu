@@ -339,6 +339,9 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   float* s_scratch = s_thi + kSlots * kTileStride;                 // kWarps * kScratch, 16-byte aligned, bank 0
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the next kernel of the stream (the emotion stream, which reads nothing this kernel writes) may take each SM as soon
+  // as this kernel's CTA leaves it, without the launch gap
+  pdl_launch_dependents();
 
   for (int i = tid; i < kFrameLen; i += kThreads) s_hann[i] = tab.hann[i];
   for (int i = tid; i < 1024; i += kThreads) s_tw[i] = tab.tw[i];
