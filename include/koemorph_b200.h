@@ -237,6 +237,36 @@ int koe_dual_stream_ring(const koe_core_weights* w, const float* power_ring, con
                          void* stream);
 
 /*
+ * One hop of every stream as ONE call (the real-time loop of scripts/rt.py:465-519 over
+ * SimplifiedDualStreamModel.process_audio_frame_realtime, src/model/simplified_dual_stream_model.py:452-500, with the
+ * sliding window of SequentialDualStreamModel.forward at stride 1): appends hop_audio to each stream's audio tail,
+ * computes the three new frames of the step (plain, window-start and window-end variants, SURVEY.md section 8 note E)
+ * into the streams' rings, and -- once window_frames hops have been pushed -- runs koe_dual_stream_ring on the window
+ * that ends at the newest sample and smooths the result (koe_ema_scan with n_out = 1).  Queues six kernels; replaces the
+ * Python driver's six separate calls (about 150 us of host time per hop).  All buffers are caller-owned device memory
+ * and persist between calls; `step` counts the hops pushed before this one (0, 1, 2, ...) and selects the ping-pong tail
+ * buffer (reads tail[step & 1], writes tail[(step + 1) & 1]) and the ring slot.  *emitted = 1 when `out` holds a frame.
+ */
+typedef struct {
+  const koe_frontend_t* frontend;
+  const koe_core_weights* weights;
+  int32_t n_streams, hop, window_frames, half_fft; /* half_fft = n_fft / 2 (512) */
+  const float* hop_audio;                          /* [n_streams][hop]: the next hop of every stream */
+  float* tail[2];                                  /* [n_streams][half_fft + hop] each; zero before the first hop */
+  float* ring_f; float* fmax_f;                    /* [n_streams][window_frames][80], [n_streams][window_frames] */
+  float* ring_r; float* fmax_r;                    /* same shapes: the window-start variants */
+  float* row_l; float* fmax_l;                     /* [n_streams][80], [n_streams]: the window-end variant */
+  const float* expr_sigmoid;                       /* [n_streams], from koe_emotion_stream */
+  float* out;                                      /* [n_streams][52] */
+  float* ema_state;                                /* [n_streams][52], or NULL: no temporal smoothing */
+  float alpha;                                     /* sigmoid(smoothing_alpha) */
+  int32_t has_state;                               /* 0 for the first emitted frame of a stream set */
+  int32_t precision;
+  int64_t step;
+} koe_stream_args;
+int koe_stream_push(const koe_stream_args* args, int* emitted, void* stream);
+
+/*
  * Learnable-alpha exponential smoothing along the frame axis, in place
  * (apply_temporal_smoothing, src/model/simplified_dual_stream_model.py:341-368):
  *   y_0 = x_0 (or alpha*x_0 + (1-alpha)*state when state != NULL and has_state != 0); y_t = alpha*x_t + (1-alpha)*y_{t-1}.

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/koemorph_b200.h"
 
@@ -50,7 +51,8 @@ inline cudaError_t launch_after_primary_starts(void (*kernel)(KArgs...), dim3 gr
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static const bool no_pdl = getenv("KOE_NO_PDL") != nullptr;  // experiment switch
+  cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -1,0 +1,93 @@
+// One streaming step as ONE native call: the hop-aligned sliding window of scripts/rt.py:465-519 /
+// SimplifiedDualStreamModel.process_audio_frame_realtime (src/model/simplified_dual_stream_model.py:452-500) for many
+// lock-step streams.  The Python driver used to issue the step as a tensor concatenation, three frontend calls, the core
+// call and the smoothing call: six kernels but ~150 us of interpreter / ctypes / allocator time per hop, a third of the
+// latency of 4096 streams and nearly all of it for a handful.  Here the six launches are queued back to back from C++.
+//
+// State per stream (all caller-owned device memory, see koe_stream_args): the last n_fft/2 + hop samples (two buffers,
+// ping-pong: step n reads tail[n & 1] and writes tail[(n + 1) & 1]), rings of W plain (F) and "window starts here" (R)
+// mel rows with their per-frame maxima, one "window ends here" row (L), the smoothing state.  SURVEY.md section 8
+// note E: frame n is centred on sample n * hop; R[n] is the same frame with everything before its centre zeroed; L[n + 1]
+// is centred on (n + 1) * hop with everything from there on zeroed.
+#include "common.cuh"
+
+namespace koe {
+
+// new_tail[s] = [old_tail[s][hop:], hop_audio[s]]: one CTA per stream row (strided over the grid), no index division
+__global__ void __launch_bounds__(256) stream_tail_shift_kernel(const float* __restrict__ old_tail,
+                                                               const float* __restrict__ hop_audio, int n_streams,
+                                                               int tail_len, int hop, float* __restrict__ new_tail) {
+  const int keep = tail_len - hop;
+  for (int s = blockIdx.x; s < n_streams; s += gridDim.x) {
+    const float* o = old_tail + (long long)s * tail_len + hop;
+    const float* x = hop_audio + (long long)s * hop;
+    float* t = new_tail + (long long)s * tail_len;
+    for (int k = threadIdx.x; k < keep; k += blockDim.x) t[k] = o[k];
+    for (int k = threadIdx.x; k < hop; k += blockDim.x) t[keep + k] = __ldcs(x + k);
+  }
+}
+
+}  // namespace koe
+
+using namespace koe;
+
+extern "C" int koe_stream_push(const koe_stream_args* a, int* emitted, void* stream_v) {
+  KOE_REQUIRE(a != nullptr && emitted != nullptr, "koe_stream_push: NULL argument");
+  KOE_REQUIRE(a->frontend != nullptr && a->weights != nullptr, "koe_stream_push: NULL frontend / weights");
+  KOE_REQUIRE(a->n_streams >= 0 && a->hop > 0 && a->window_frames > 0 && a->half_fft > 0 && a->step >= 0,
+              "koe_stream_push: bad geometry");
+  KOE_REQUIRE(a->hop >= a->half_fft, "koe_stream_push: implements the hop >= n_fft/2 geometry (one edge frame per window side)");
+  KOE_REQUIRE(a->hop_audio && a->tail[0] && a->tail[1] && a->ring_f && a->fmax_f && a->ring_r && a->fmax_r && a->row_l &&
+                  a->fmax_l && a->expr_sigmoid && a->out,
+              "koe_stream_push: NULL buffer");
+  *emitted = 0;
+  if (a->n_streams == 0) return KOE_OK;
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  const int S = a->n_streams, hop = a->hop, W = a->window_frames, half = a->half_fft, tail_len = half + hop;
+  const int64_t n = a->step;
+  const float* old_tail = a->tail[n & 1];
+  float* tail = a->tail[(n + 1) & 1];
+  {
+    const int grid = std::min(S, 148 * 8);
+    stream_tail_shift_kernel<<<grid, 256, 0, stream>>>(old_tail, a->hop_audio, S, tail_len, hop, tail);
+    count_launch();
+    KOE_CUDA(cudaGetLastError());
+  }
+  const int slot = (int)(n % W);
+  koe_logmel_args f = {};
+  f.audio = tail;
+  f.audio_stride = tail_len;
+  f.n_clips = S;
+  f.n_samples = tail_len;
+  f.hop = hop;
+  f.n_frames = 1;
+  f.frame_offset = 0;
+  f.frame_step = 1;
+  f.pad_mode = 0;
+  // F[n]: centred on local sample `half`; before the first hop the tail is zeros = librosa's zero padding
+  f.sample_offset = half;
+  f.lo_rel_hops = KOE_NO_EDGE, f.hi_rel_hops = KOE_NO_EDGE;
+  f.power = a->ring_f + (size_t)slot * KOE_N_MELS, f.power_clip_stride = (int64_t)W * KOE_N_MELS;
+  f.frame_max = a->fmax_f + slot, f.frame_max_clip_stride = W;
+  if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+  // R[n]: the same frame, nothing before its centre
+  f.lo_rel_hops = 0;
+  f.power = a->ring_r + (size_t)slot * KOE_N_MELS;
+  f.frame_max = a->fmax_r + slot;
+  if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+  // L[n + 1]: centred on the end of the tail, nothing from its centre on
+  f.sample_offset = tail_len;
+  f.lo_rel_hops = KOE_NO_EDGE, f.hi_rel_hops = 0;
+  f.power = a->row_l, f.power_clip_stride = KOE_N_MELS;
+  f.frame_max = a->fmax_l, f.frame_max_clip_stride = 1;
+  if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+  if (n + 1 < W) return KOE_OK;  // the 8.5 s context is not full yet
+  const int base = (int)((n + 1 - W) % W);  // ring slot of the first frame of the window that ends now
+  if (int rc = koe_dual_stream_ring(a->weights, a->ring_f, a->fmax_f, a->ring_r, a->fmax_r, a->row_l, a->fmax_l, S, W, base,
+                                    W + 1, a->expr_sigmoid, a->out, nullptr, nullptr, a->precision, stream))
+    return rc;
+  if (a->ema_state != nullptr)
+    if (int rc = koe_ema_scan(a->out, S, 1, a->alpha, a->ema_state, a->has_state, stream)) return rc;
+  *emitted = 1;
+  return KOE_OK;
+}

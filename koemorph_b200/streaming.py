@@ -35,12 +35,13 @@ class StreamingEngine:
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("StreamingEngine needs the model on a CUDA device")
+        self._dev_index = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
         self.hop = model.hop_length
         self.W = model.mel_sequence_length
         self.half = model.n_fft // 2
         self.tail_len = self.half + self.hop               # samples [ (n+1)hop - tail_len, (n+1)hop )
         f32 = dict(dtype=torch.float32, device=self.dev)
-        self.tail = torch.zeros(self.S, self.tail_len, **f32)
+        self._tails = [torch.zeros(self.S, self.tail_len, **f32) for _ in range(2)]   # ping-pong (koe_stream_push)
         self.ring_f = torch.zeros(self.S, self.W, 80, **f32)
         self.ring_r = torch.zeros(self.S, self.W, 80, **f32)
         self.fmax_f = torch.zeros(self.S, self.W, **f32)
@@ -54,18 +55,22 @@ class StreamingEngine:
         self.emitted = 0
         self._fe = model._frontend(self.dev)
         self._alpha, self._alpha_key = 0.0, None
+        self._args, self._args_key, self._w_tensors = None, None, []
+        self.native = True                                  # one koe_stream_push per step (False: call by call from Python)
 
     def reset(self):
-        for t in (self.tail, self.ring_f, self.ring_r, self.fmax_f, self.fmax_r, self.state):
+        for t in (*self._tails, self.ring_f, self.ring_r, self.fmax_f, self.fmax_r, self.state):
             t.zero_()
         self.n = 0
         self.emitted = 0
+        self._args = None                                   # the next step walks the module's weights again
 
     @torch.no_grad()
     def set_egemaps(self, egemaps: torch.Tensor) -> None:
         """(S, 264) eGeMAPS windows; the reference refreshes them every 300 ms, not every frame
         (src/features/opensmile_extractor.py:168)."""
         eg = self.model._check_egemaps(egemaps, self.S, self.dev)
+        self._args = None                                   # (a natural point to pick up replaced weights, too)
         w = self.model.dual_stream_attention.kernel_weights(self.model._compression)
         with torch.cuda.device(self.dev):
             _lib.check(_lib.load().koe_emotion_stream(C.byref(w.struct), eg.data_ptr(), self.S, self.expr.data_ptr(),
@@ -78,17 +83,80 @@ class StreamingEngine:
         x = _lib.require_cuda(hop_audio, "hop_audio")
         if x.shape != (self.S, self.hop):
             raise ValueError(f"hop_audio must be ({self.S}, {self.hop}), got {tuple(x.shape)}")
+        if not self.native:
+            return self._step_python(x)
+        # the whole step -- tail shift, the three new frames F[n], R[n], L[n+1] into the rings, the window that ends at
+        # the newest sample through the core, the smoothing -- is one native call that queues six kernels
+        # (host time before the first launch is latency nobody hides: the argument block is built once, a step only
+        # updates what changes)
+        m = self.model
+        a = self._args
+        # the folded weights are re-validated against the module's parameters by their in-place version counters every
+        # step, and by the full walk over the module (replaced tensors: .to(), new Parameters) every 256th
+        key = (m.precision, m.use_temporal_smoothing, tuple(t._version for t in self._w_tensors))
+        if a is None or self._args_key != key or (self.n & 255) == 0:
+            a = self._args = self._build_args()
+            self._args_key = (m.precision, m.use_temporal_smoothing, tuple(t._version for t in self._w_tensors))
+        if m.use_temporal_smoothing:
+            # sigmoid(smoothing_alpha) is read back once per parameter version, not once per hop (a device sync)
+            ver = (m.smoothing_alpha.data_ptr(), m.smoothing_alpha._version)
+            if self._alpha_key != ver:
+                self._alpha = float(torch.sigmoid(m.smoothing_alpha.detach().float()))
+                self._alpha_key = ver
+            a.alpha = self._alpha
+        a.hop_audio = x.data_ptr()
+        a.has_state = 1 if self.emitted > 0 else 0
+        a.step = self.n
+        emitted = self._emitted_flag
+        if torch.cuda.current_device() == self._dev_index:
+            rc = self._push(self._args_ref, self._emitted_ref, torch.cuda.current_stream(self.dev).cuda_stream)
+        else:
+            with torch.cuda.device(self.dev):
+                rc = self._push(self._args_ref, self._emitted_ref, torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(rc, "koe_stream_push")
+        self.n += 1
+        if not emitted.value:
+            return None
+        self.emitted += 1
+        return self.out
+
+    def _build_args(self):
+        m = self.model
+        self._weights = m.dual_stream_attention.kernel_weights(m._compression)   # (kept alive: the block points into it)
+        att = m.dual_stream_attention
+        self._w_tensors = [t for _, t in att.named_parameters()] + [t for _, t in att.named_buffers()] + \
+            ([] if m._compression is None else [m._compression["weight"], m._compression["bias"]])
+        a = _lib.StreamArgs()
+        a.frontend, a.weights = self._fe._h, C.cast(C.pointer(self._weights.struct), C.c_void_p)
+        a.n_streams, a.hop, a.window_frames, a.half_fft = self.S, self.hop, self.W, self.half
+        a.tail[0], a.tail[1] = self._tails[0].data_ptr(), self._tails[1].data_ptr()
+        a.ring_f, a.fmax_f = self.ring_f.data_ptr(), self.fmax_f.data_ptr()
+        a.ring_r, a.fmax_r = self.ring_r.data_ptr(), self.fmax_r.data_ptr()
+        a.row_l, a.fmax_l = self.row_l.data_ptr(), self.fmax_l.data_ptr()
+        a.expr_sigmoid, a.out = self.expr.data_ptr(), self.out.data_ptr()
+        a.ema_state, a.alpha = (self.state.data_ptr(), self._alpha) if m.use_temporal_smoothing else (None, 1.0)
+        a.precision = _lib.PRECISIONS[m.precision]
+        self._args_ref = C.byref(a)
+        self._emitted_flag = C.c_int(0)
+        self._emitted_ref = C.byref(self._emitted_flag)
+        self._push = _lib.load().koe_stream_push
+        return a
+
+    def _step_python(self, x: torch.Tensor) -> Optional[torch.Tensor]:
+        """The same step issued call by call from Python (``native = False``): the readable statement of what
+        koe_stream_push does, kept as its cross-check (tests/test_gpu_streaming.py)."""
         n, hop, W, half = self.n, self.hop, self.W, self.half
         # slide the audio tail: keep the last n_fft/2 samples, append the hop
-        self.tail = torch.cat([self.tail[:, hop:], x], dim=1)
+        tail = self._tails[(n + 1) & 1]
+        torch.cat([self._tails[n & 1][:, hop:], x], dim=1, out=tail)
         slot = n % W
         fe = self._fe
         # F[n]: centred on local sample `half`; before the first hop the tail is zeros = librosa's zero padding
-        fe.power(self.tail, hop, 1, sample_offset=half, out=(self.ring_f, self.fmax_f), out_row=slot)
+        fe.power(tail, hop, 1, sample_offset=half, out=(self.ring_f, self.fmax_f), out_row=slot)
         # R[n]: same frame, nothing before its centre
-        fe.power(self.tail, hop, 1, sample_offset=half, lo_rel=0, out=(self.ring_r, self.fmax_r), out_row=slot)
+        fe.power(tail, hop, 1, sample_offset=half, lo_rel=0, out=(self.ring_r, self.fmax_r), out_row=slot)
         # L[n+1]: centred on the end of the tail, nothing from its centre on
-        fe.power(self.tail, hop, 1, sample_offset=self.tail_len, hi_rel=0, out=(self.row_l, self.fmax_l))
+        fe.power(tail, hop, 1, sample_offset=self.tail_len, hi_rel=0, out=(self.row_l, self.fmax_l))
         self.n += 1
         if self.n < W:
             return None

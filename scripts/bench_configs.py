@@ -69,6 +69,7 @@ def c4(dev, args):
     m = make_model(30, dev, args.precision)
     S = args.streams
     eng = StreamingEngine(m, S)
+    eng.native = not args.stream_python_driver
     eng.set_egemaps(torch.randn(S, 264, device=dev))
     hops = [0.1 * torch.randn(S, m.hop_length, device=dev) for _ in range(8)]
     for i in range(m.mel_sequence_length + 8):          # fill the 8.5 s context, then a few emitting warm-up steps
@@ -87,6 +88,7 @@ def c4(dev, args):
             "latency_ms": {"p50": p(0.50), "p90": p(0.90), "p99": p(0.99), "max": lat[-1], "steps": len(lat)},
             "value": S * (m.hop_length / 16000.0) / (p(0.50) * 1e-3), "unit": "audio-s/s (new audio per wall second at p50)",
             "real_time_factor_p99": (m.hop_length / 16000.0 * 1e3) / p(0.99), "n_gpus": 1,
+            "driver": "koe_stream_push (one native call per step)" if eng.native else "six calls per step from Python",
             "note": "latency = host submit of one hop for every stream -> all outputs complete on the device (host sync)"}
 
 
@@ -128,6 +130,8 @@ def c5(dev, args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c3,c4,c5")
+    ap.add_argument("--stream-python-driver", action="store_true",
+                    help="c4: issue the step call by call from Python instead of through koe_stream_push")
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--stream-steps", type=int, default=300)
     ap.add_argument("--corpus-clips", type=int, default=1000000)

@@ -118,3 +118,37 @@ def test_streaming_engine_bf16_and_realtime_model():
     assert res.shape == (52,) and bool(torch.isfinite(res).all())
     assert "mel_stats" in rt.get_realtime_stats()
     rt.reset_realtime_state()
+
+
+def test_native_stream_step_equals_the_call_by_call_driver():
+    """koe_stream_push (one native call per hop: tail shift, three frontend launches, the core, the smoothing) against
+    the same step issued call by call from Python: every emitted frame bit for bit, and the persistent state with it."""
+    import koemorph_b200 as K
+    from koemorph_b200.streaming import StreamingEngine
+    w = O.make_weights(77, 30, style="stress")
+    m = K.SequentialDualStreamModel().cuda().eval()
+    m.load_state_dict(O.model_state_dict(w), strict=True)
+    m.set_compression_layer(torch.from_numpy(w["compression.weight"]), torch.from_numpy(w["compression.bias"]))
+    S, steps = 3, 256 + 7
+    audio, eg = O.make_inputs(5, S, steps * 533, "speechlike")
+    a, e = torch.from_numpy(audio).cuda(), torch.from_numpy(eg).cuda()
+    engines = []
+    for native in (True, False):
+        eng = StreamingEngine(m, S)
+        eng.native = native
+        eng.set_egemaps(e)
+        engines.append(eng)
+    emitted = 0
+    for n in range(steps):
+        hop = a[:, n * 533:(n + 1) * 533].contiguous()
+        o_native, o_python = engines[0].step(hop), engines[1].step(hop)
+        assert (o_native is None) == (o_python is None) == (n + 1 < 256)
+        if o_native is not None:
+            emitted += 1
+            assert torch.equal(o_native, o_python), f"hop {n}"
+    assert emitted == 8
+    for name in ("ring_f", "ring_r", "fmax_f", "fmax_r", "row_l", "fmax_l", "state"):
+        assert torch.equal(getattr(engines[0], name), getattr(engines[1], name)), name
+    # reset() starts both from silence again
+    engines[0].reset()
+    assert engines[0].step(a[:, :533].contiguous()) is None and engines[0].n == 1
