@@ -119,6 +119,14 @@ typedef struct {
   int64_t power_clip_stride;
   float* frame_max;
   int64_t frame_max_clip_stride;
+  /* optional second destination: when power_b != NULL the odd frames (2j + 1, the second frame of every pair the kernel
+   * transforms together) are written to power_b[clip][j] / frame_max_b[clip][j] instead of row 2j + 1 of `power`.  The
+   * streaming step uses it with n_frames = 2: the new plain frame goes into the stream's ring, the next hop's
+   * "window ends here" frame (same launch, same transform) into its own row. */
+  float* power_b;
+  int64_t power_b_clip_stride;
+  float* frame_max_b;
+  int64_t frame_max_b_clip_stride;
 } koe_logmel_args;
 int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_args* args, void* stream);
 
@@ -242,7 +250,7 @@ int koe_dual_stream_ring(const koe_core_weights* w, const float* power_ring, con
  * sliding window of SequentialDualStreamModel.forward at stride 1): appends hop_audio to each stream's audio tail,
  * computes the three new frames of the step (plain, window-start and window-end variants, SURVEY.md section 8 note E)
  * into the streams' rings, and -- once window_frames hops have been pushed -- runs koe_dual_stream_ring on the window
- * that ends at the newest sample and smooths the result (koe_ema_scan with n_out = 1).  Queues six kernels; replaces the
+ * that ends at the newest sample and smooths the result (koe_ema_scan with n_out = 1).  Queues five kernels; replaces the
  * Python driver's six separate calls (about 150 us of host time per hop).  All buffers are caller-owned device memory
  * and persist between calls; `step` counts the hops pushed before this one (0, 1, 2, ...) and selects the ping-pong tail
  * buffer (reads tail[step & 1], writes tail[(step + 1) & 1]) and the ring slot.  *emitted = 1 when `out` holds a frame.

@@ -44,6 +44,8 @@ class LogmelArgs(C.Structure):
         ("lo_rel_hops", C.c_int32), ("hi_rel_hops", C.c_int32), ("pad_mode", C.c_int32),
         ("power", C.c_void_p), ("power_clip_stride", C.c_int64),
         ("frame_max", C.c_void_p), ("frame_max_clip_stride", C.c_int64),
+        ("power_b", C.c_void_p), ("power_b_clip_stride", C.c_int64),
+        ("frame_max_b", C.c_void_p), ("frame_max_b_clip_stride", C.c_int64),
     ]
 
 

@@ -66,6 +66,9 @@ struct LogmelParams {
   float* power;
   float* frame_max;
   long long power_clip_stride, fmax_clip_stride;  // elements between consecutive clips' output blocks
+  float* power_b;                // optional: odd frames 2j+1 go to power_b[clip][j] / frame_max_b[clip][j] instead
+  float* frame_max_b;
+  long long power_b_clip_stride, fmax_b_clip_stride;
   int edge_lo, edge_hi;          // leading / trailing frame pairs of a clip that need masked loads (launch order only)
 };
 
@@ -325,7 +328,9 @@ __device__ __forceinline__ void mel_phase_generic(int g, int gend, const int4* s
   }
 }
 
-template <bool kDefaultBank>
+// kSplitB: the pairs' second frames go to their own buffer (LogmelParams::power_b; the streaming step) -- a separate
+// instantiation so that the batch kernel carries none of it (the extra pointer arithmetic cost it 3 us of 179)
+template <bool kDefaultBank, bool kSplitB = false>
 __global__ void __launch_bounds__(kThreads, 1)
 logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -458,19 +463,27 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
       }
       float mx_a = fmaxf(db[0], db[1]), mx_b = fmaxf(db[3], db[4]);
       if (lane < KOE_N_MELS - 64) mx_a = fmaxf(mx_a, db[2]); else mx_b = fmaxf(mx_b, db[2]);
+      // row B follows row A, or goes to its own buffer (power_b: pair j of the clip -> row j there); dst_b is biased by
+      // one row so that the same indices address it
+      float* dst_b = dst;
+      if constexpr (kSplitB)
+        dst_b = p.power_b + (long long)cur.clip * p.power_b_clip_stride + (long long)(cur.frame >> 1) * KOE_N_MELS - KOE_N_MELS;
       dst[lane] = db[0];
       dst[lane + 32] = db[1];
-      if (cur.has_b || lane < KOE_N_MELS - 64) dst[lane + 64] = db[2];
+      float* dst_mid = lane < KOE_N_MELS - 64 ? dst : dst_b;  // the third 32-value piece straddles the two rows
+      if (cur.has_b || lane < KOE_N_MELS - 64) dst_mid[lane + 64] = db[2];
       if (cur.has_b) {
-        dst[lane + 96] = db[3];
-        dst[lane + 128] = db[4];
+        dst_b[lane + 96] = db[3];
+        dst_b[lane + 128] = db[4];
       }
       if (p.frame_max != nullptr) {
         const int ia = __reduce_max_sync(kFullMask, float_order(mx_a));
         const int ib = __reduce_max_sync(kFullMask, float_order(mx_b));
         float* fm = p.frame_max + (long long)cur.clip * p.fmax_clip_stride + cur.frame;
+        float* fm_b = fm;
+        if constexpr (kSplitB) fm_b = p.frame_max_b + (long long)cur.clip * p.fmax_b_clip_stride + (cur.frame >> 1) - 1;
         if (lane == 0) fm[0] = order_float(ia);
-        if (lane == 1 && cur.has_b) fm[1] = order_float(ib);
+        if (lane == 1 && cur.has_b) fm_b[1] = order_float(ib);
       }
     }
   }
@@ -771,6 +784,10 @@ extern "C" int koe_frontend_create_ex(const koe_frontend_config* cfg, koe_fronte
     e = cudaFuncSetAttribute(logmel_power_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelSmem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(logmel_power_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(logmel_power_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(logmel_power_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelSmem);
   cudaDeviceProp prop;
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) {
@@ -852,6 +869,12 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
   p.frame_max = a->frame_max;
   p.power_clip_stride = a->power_clip_stride;
   p.fmax_clip_stride = a->frame_max_clip_stride;
+  p.power_b = a->power_b;
+  p.power_b_clip_stride = a->power_b_clip_stride;
+  p.frame_max_b = a->frame_max_b;
+  p.fmax_b_clip_stride = a->frame_max_b_clip_stride;
+  KOE_REQUIRE(a->power_b == nullptr || (a->frame_max == nullptr) == (a->frame_max_b == nullptr),
+              "koe_logmel_power_ex: power_b needs frame_max_b whenever frame_max is given");
   {
     const int ppc = (p.n_frames + 1) / 2;
     p.edge_lo = 0;
@@ -864,7 +887,12 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
   const long long n_blocks = ((long long)a->n_clips * ppc + kWarps - 1) / kWarps;
   const long long max_grid = (long long)fe->num_sms * fe->occupancy;
   const int grid = (int)std::min(n_blocks, max_grid);
-  if (fe->default_bank)
+  if (p.power_b != nullptr) {
+    if (fe->default_bank)
+      logmel_power_kernel<true, true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
+    else
+      logmel_power_kernel<false, true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
+  } else if (fe->default_bank)
     logmel_power_kernel<true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
   else
     logmel_power_kernel<false><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
@@ -876,7 +904,7 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
 extern "C" int koe_logmel_power(const koe_frontend_t* fe, const float* audio, int64_t audio_stride, int n_clips,
                                 int n_samples, int hop, int n_frames, int frame_offset, int frame_step,
                                 int lo_rel_hops, int hi_rel_hops, float* power, float* frame_max, void* stream) {
-  koe_logmel_args a;
+  koe_logmel_args a = {};
   a.audio = audio;
   a.audio_stride = audio_stride;
   a.n_clips = n_clips;

@@ -2,7 +2,7 @@
 // SimplifiedDualStreamModel.process_audio_frame_realtime (src/model/simplified_dual_stream_model.py:452-500) for many
 // lock-step streams.  The Python driver used to issue the step as a tensor concatenation, three frontend calls, the core
 // call and the smoothing call: six kernels but ~150 us of interpreter / ctypes / allocator time per hop, a third of the
-// latency of 4096 streams and nearly all of it for a handful.  Here the six launches are queued back to back from C++.
+// latency of 4096 streams and nearly all of it for a handful.  Here the five launches are queued back to back from C++.
 //
 // State per stream (all caller-owned device memory, see koe_stream_args): the last n_fft/2 + hop samples (two buffers,
 // ping-pong: step n reads tail[n & 1] and writes tail[(n + 1) & 1]), rings of W plain (F) and "window starts here" (R)
@@ -64,22 +64,24 @@ extern "C" int koe_stream_push(const koe_stream_args* a, int* emitted, void* str
   f.frame_offset = 0;
   f.frame_step = 1;
   f.pad_mode = 0;
-  // F[n]: centred on local sample `half`; before the first hop the tail is zeros = librosa's zero padding
+  // F[n] and L[n + 1] are consecutive frames of the tail (centres `half` and `half + hop` = the end of the tail, beyond
+  // which the clip reads as zeros: exactly the "nothing from its centre on" of L), so ONE launch transforms them as one
+  // pair; F goes to the ring slot, L (the pair's second frame) to its own row.  Before the first hop the tail is zeros =
+  // librosa's zero padding.
+  f.n_frames = 2;
   f.sample_offset = half;
   f.lo_rel_hops = KOE_NO_EDGE, f.hi_rel_hops = KOE_NO_EDGE;
   f.power = a->ring_f + (size_t)slot * KOE_N_MELS, f.power_clip_stride = (int64_t)W * KOE_N_MELS;
   f.frame_max = a->fmax_f + slot, f.frame_max_clip_stride = W;
+  f.power_b = a->row_l, f.power_b_clip_stride = KOE_N_MELS;
+  f.frame_max_b = a->fmax_l, f.frame_max_b_clip_stride = 1;
   if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
-  // R[n]: the same frame, nothing before its centre
+  // R[n]: frame n again, nothing before its centre
+  f.n_frames = 1;
   f.lo_rel_hops = 0;
   f.power = a->ring_r + (size_t)slot * KOE_N_MELS;
   f.frame_max = a->fmax_r + slot;
-  if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
-  // L[n + 1]: centred on the end of the tail, nothing from its centre on
-  f.sample_offset = tail_len;
-  f.lo_rel_hops = KOE_NO_EDGE, f.hi_rel_hops = 0;
-  f.power = a->row_l, f.power_clip_stride = KOE_N_MELS;
-  f.frame_max = a->fmax_l, f.frame_max_clip_stride = 1;
+  f.power_b = nullptr, f.frame_max_b = nullptr;
   if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
   if (n + 1 < W) return KOE_OK;  // the 8.5 s context is not full yet
   const int base = (int)((n + 1 - W) % W);  // ring slot of the first frame of the window that ends now

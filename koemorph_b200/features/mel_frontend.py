@@ -94,12 +94,14 @@ class LogMelFrontend:
     def power(self, audio: torch.Tensor, hop: int, n_frames: int, frame_offset: int = 0, frame_step: int = 1,
               lo_rel: Optional[int] = None, hi_rel: Optional[int] = None,
               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, sample_offset: int = 0,
-              pad_mode: str = "constant", out_row: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+              pad_mode: str = "constant", out_row: int = 0,
+              out_b: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """audio (B, L) float32 CUDA -> mel power in dB, 10*log10(max(p, 1e-10)), (B, n_frames, 80) and its
         per-frame max (B, n_frames).
 
         With ``out=(power, fmax)`` of shapes (B, R, 80) / (B, R) the n_frames rows are written at rows
-        ``out_row ...`` of every clip's block (ring buffers of the streaming paths)."""
+        ``out_row ...`` of every clip's block (ring buffers of the streaming paths).  With ``out_b=(power_b, fmax_b)`` of
+        shapes (B, Rb, 80) / (B, Rb) the odd frames 2j + 1 go to row j there instead (koe_logmel_args.power_b)."""
         audio = _lib.require_cuda(audio, "audio")
         if audio.dim() != 2:
             raise ValueError(f"audio must be (B, L), got {tuple(audio.shape)}")
@@ -111,7 +113,8 @@ class LogMelFrontend:
             fmax = torch.empty((B, n_frames), dtype=torch.float32, device=audio.device)
         else:
             power, fmax = out
-            if power.shape[0] != B or power.shape[2] != self.n_mels or out_row + n_frames > power.shape[1] or \
+            rows = n_frames if out_b is None else 2 * ((n_frames - 1) // 2) + 1   # with out_b only the even frames land here
+            if power.shape[0] != B or power.shape[2] != self.n_mels or out_row + rows > power.shape[1] or \
                     fmax.shape[:2] != power.shape[:2] or not power.is_contiguous() or not fmax.is_contiguous():
                 raise ValueError("out must be contiguous (B, R, 80) / (B, R) tensors with out_row + n_frames <= R")
         a = _lib.LogmelArgs()
@@ -125,6 +128,13 @@ class LogMelFrontend:
         a.power_clip_stride = power.stride(0)
         a.frame_max = fmax.data_ptr() + out_row * 4
         a.frame_max_clip_stride = fmax.stride(0)
+        if out_b is not None:
+            pb, fb = out_b
+            if pb.shape[0] != B or pb.shape[2] != self.n_mels or pb.shape[1] < n_frames // 2 or \
+                    fb.shape[:2] != pb.shape[:2] or not pb.is_contiguous() or not fb.is_contiguous():
+                raise ValueError("out_b must be contiguous (B, Rb, 80) / (B, Rb) tensors with n_frames // 2 <= Rb")
+            a.power_b, a.power_b_clip_stride = pb.data_ptr(), pb.stride(0)
+            a.frame_max_b, a.frame_max_b_clip_stride = fb.data_ptr(), fb.stride(0)
         with torch.cuda.device(audio.device):
             _lib.check(self._lib.koe_logmel_power_ex(self._h, C.byref(a), _lib.stream_ptr(audio.device)),
                        "koe_logmel_power")

@@ -86,7 +86,7 @@ class StreamingEngine:
         if not self.native:
             return self._step_python(x)
         # the whole step -- tail shift, the three new frames F[n], R[n], L[n+1] into the rings, the window that ends at
-        # the newest sample through the core, the smoothing -- is one native call that queues six kernels
+        # the newest sample through the core, the smoothing -- is one native call that queues five kernels
         # (host time before the first launch is latency nobody hides: the argument block is built once, a step only
         # updates what changes)
         m = self.model
@@ -151,12 +151,12 @@ class StreamingEngine:
         torch.cat([self._tails[n & 1][:, hop:], x], dim=1, out=tail)
         slot = n % W
         fe = self._fe
-        # F[n]: centred on local sample `half`; before the first hop the tail is zeros = librosa's zero padding
-        fe.power(tail, hop, 1, sample_offset=half, out=(self.ring_f, self.fmax_f), out_row=slot)
-        # R[n]: same frame, nothing before its centre
+        # F[n] and L[n+1] are consecutive frames of the tail (L is centred on its end, beyond which the clip reads as
+        # zeros): one launch, F into the ring slot, L (the pair's second frame) into its own row
+        fe.power(tail, hop, 2, sample_offset=half, out=(self.ring_f, self.fmax_f), out_row=slot,
+                 out_b=(self.row_l, self.fmax_l))
+        # R[n]: frame n again, nothing before its centre
         fe.power(tail, hop, 1, sample_offset=half, lo_rel=0, out=(self.ring_r, self.fmax_r), out_row=slot)
-        # L[n+1]: centred on the end of the tail, nothing from its centre on
-        fe.power(tail, hop, 1, sample_offset=self.tail_len, hi_rel=0, out=(self.row_l, self.fmax_l))
         self.n += 1
         if self.n < W:
             return None
