@@ -41,6 +41,9 @@ extern "C" {
 
 const char* koe_last_error(void);
 int koe_version(void);
+/* sizeof of the public argument structs, for bindings that mirror them (ctypes, cgo, JNI): 0 koe_frontend_config,
+ * 1 koe_logmel_args, 2 koe_core_weights, 3 koe_stream_args; -1 for any other index */
+int koe_sizeof_struct(int which);
 /* number of kernels launched by this library in this process since load / since the last reset */
 int64_t koe_launch_count(void);
 void koe_reset_launch_count(void);

@@ -129,3 +129,14 @@ def test_numa_binding_helper_is_a_no_op_without_topology():
     assert bind_host_thread_to_gpu_node(0) in (None, 0, 1, 2, 3)
     if not __import__("torch").cuda.is_available():
         assert os.sched_getaffinity(0) == before
+
+
+def test_ctypes_mirrors_have_the_size_of_the_c_structs():
+    """The argument blocks cross the C ABI by pointer: a ctypes mirror that drifts from include/koemorph_b200.h would
+    scribble over the fields behind the drift (the library reports its own sizeof for exactly this check)."""
+    import ctypes as C
+    from koemorph_b200 import _lib
+    lib = _lib.load()
+    for which, mirror in enumerate((_lib.FrontendConfig, _lib.LogmelArgs, _lib.CoreWeightsStruct, _lib.StreamArgs)):
+        assert lib.koe_sizeof_struct(which) == C.sizeof(mirror), mirror.__name__
+    assert lib.koe_sizeof_struct(99) == -1
