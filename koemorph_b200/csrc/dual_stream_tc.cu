@@ -583,29 +583,13 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
             for (int e = 0; e < 8; ++e) {
               const int t = 8 * c + e;
               float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+              // (this branch serves the prenormalised-features entry point only: raw mel power always comes through the
+              // TMA mel ring above)
               if (t < kKMel) {
-                if (prenorm) {
-                  if (t >= p.mel_seq)
-                    x = __ldg(reinterpret_cast<const float4*>(p.mel_short + ((size_t)b * 3 + (t - p.mel_seq)) * kTok) + q);
-                  else if (t < p.n_long)
-                    x = __ldg(reinterpret_cast<const float4*>(p.mel_long + ((size_t)b * p.n_frames + t) * kTok) + q);
-                } else {
-                  int k;
-                  if (t < p.mel_seq)
-                    k = t < T ? t : -1;
-                  else {
-                    const int s = t - p.mel_seq;
-                    k = T >= 3 ? T - 3 + s : (s < T ? s : -1);
-                  }
-                  if (k >= 0) {
-                    const int var = window_variant(p, k);
-                    x = __ldg(reinterpret_cast<const float4*>(p.power[var] + window_row(p, var, b, wi, k) * kTok) + q);
-                  } else {
-                    x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);  // zero padding: normalises to 0
-                  }
-                }
-              } else if (!prenorm) {
-                x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                if (t >= p.mel_seq)
+                  x = __ldg(reinterpret_cast<const float4*>(p.mel_short + ((size_t)b * 3 + (t - p.mel_seq)) * kTok) + q);
+                else if (t < p.n_long)
+                  x = __ldg(reinterpret_cast<const float4*>(p.mel_long + ((size_t)b * p.n_frames + t) * kTok) + q);
               }
               r[e] = x;
             }
@@ -615,15 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
             float v[4][8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              if (prenorm) {
-                v[0][e] = r[e].x, v[1][e] = r[e].y, v[2][e] = r[e].z, v[3][e] = r[e].w;
-              } else {
-                const bool real = 8 * c + e < kKMel;       // the K tail past the bias column must be exact zeros
-                v[0][e] = real ? normalise_bf16(r[e].x, ref_db, true) : 0.0f;
-                v[1][e] = real ? normalise_bf16(r[e].y, ref_db, true) : 0.0f;
-                v[2][e] = real ? normalise_bf16(r[e].z, ref_db, true) : 0.0f;
-                v[3][e] = real ? normalise_bf16(r[e].w, ref_db, true) : 0.0f;
-              }
+              v[0][e] = r[e].x, v[1][e] = r[e].y, v[2][e] = r[e].z, v[3][e] = r[e].w;
               if (8 * c + e == kKMel)  // operand column k_mel: multiplies the encoder-bias row of the weights
                 v[0][e] = v[1][e] = v[2][e] = v[3][e] = 1.0f;
             }
