@@ -143,3 +143,29 @@ def test_fp64_oracle_agrees_with_fp32():
     b = O.forward_single(w, audio, eg, dtype=torch.float64)
     assert (a["blendshapes"].double() - b["blendshapes"]).abs().max() < 1e-6
     assert (a["sigmoid"].double() - b["sigmoid"]).abs().max() < 1e-5
+
+
+def test_librosa_stage_vs_transformers_audio_utils():
+    """A third independent implementation of the librosa stage: transformers.audio_utils (numpy; written to reproduce
+    librosa's Slaney filterbank, centred STFT and power_to_db for the Whisper-family feature extractors).  Filterbank,
+    mel power and the dB conversion of the oracle's restatement against it, on a speech-like clip."""
+    A = pytest.importorskip("transformers.audio_utils")
+    fb = A.mel_filter_bank(num_frequency_bins=513, num_mel_filters=80, min_frequency=80.0, max_frequency=8000.0,
+                           sampling_rate=16000, norm="slaney", mel_scale="slaney")            # (513, 80) float64
+    ours = O.mel_filterbank().astype(np.float64)                                              # (80, 513) float32 weights
+    assert np.abs(ours - fb.T).max() <= 2e-7 * fb.max()
+    assert ((ours > 0) == (fb.T > 1e-12)).all()
+
+    audio, _ = O.make_inputs(17, 1, 40000, "speechlike")
+    y = audio[0]
+    window = A.window_function(1024, "hann", periodic=True) if hasattr(A, "window_function") else O.hann_window(1024)
+    mel = A.spectrogram(y.astype(np.float64), window, frame_length=1024, hop_length=533, power=2.0, center=True,
+                        pad_mode="constant", mel_filters=fb, mel_floor=0.0, dtype=np.float64)    # (80, T)
+    ref = O.melspectrogram(y, hop_length=533, exact=True)                                       # float64 restatement
+    assert mel.shape == ref.shape == (80, 1 + 40000 // 533)
+    # (librosa -- and the restatement -- keep the filterbank in float32; audio_utils keeps float64: 6e-8 relative)
+    assert np.abs(mel - ref).max() <= 2e-7 * ref.max()
+
+    db = A.power_to_db(mel, reference=mel.max(), min_value=1e-10, db_range=80.0)
+    ours_db = O.power_to_db(ref.astype(np.float64))
+    assert np.abs(db - ours_db).max() <= 2e-5   # dB; 2e-7 relative in power is 1e-6 dB, the rest is the -80 dB clamp edge
