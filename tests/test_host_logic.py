@@ -140,3 +140,17 @@ def test_ctypes_mirrors_have_the_size_of_the_c_structs():
     for which, mirror in enumerate((_lib.FrontendConfig, _lib.LogmelArgs, _lib.CoreWeightsStruct, _lib.StreamArgs)):
         assert lib.koe_sizeof_struct(which) == C.sizeof(mirror), mirror.__name__
     assert lib.koe_sizeof_struct(99) == -1
+
+
+def test_public_header_is_plain_c():
+    """include/koemorph_b200.h is the contract a cgo / JNI / ctypes binding compiles against: it must parse as C99 on
+    its own (no C++ types, no CUDA or torch headers)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler here")
+    header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "koemorph_b200.h")
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", header],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
