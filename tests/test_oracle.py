@@ -149,7 +149,15 @@ def test_librosa_stage_vs_transformers_audio_utils():
     """A third independent implementation of the librosa stage: transformers.audio_utils (numpy; written to reproduce
     librosa's Slaney filterbank, centred STFT and power_to_db for the Whisper-family feature extractors).  Filterbank,
     mel power and the dB conversion of the oracle's restatement against it, on a speech-like clip."""
-    A = pytest.importorskip("transformers.audio_utils")
+    # (the live-reference test above leaves stand-in `librosa` / `opensmile` modules in sys.modules; transformers probes
+    # for librosa with importlib.util.find_spec, which rejects a module without a spec)
+    import sys
+    parked = {k: sys.modules.pop(k) for k in ("librosa", "opensmile")
+              if k in sys.modules and getattr(sys.modules[k], "__spec__", None) is None}
+    try:
+        A = pytest.importorskip("transformers.audio_utils")
+    finally:
+        sys.modules.update(parked)
     fb = A.mel_filter_bank(num_frequency_bins=513, num_mel_filters=80, min_frequency=80.0, max_frequency=8000.0,
                            sampling_rate=16000, norm="slaney", mel_scale="slaney")            # (513, 80) float64
     ours = O.mel_filterbank().astype(np.float64)                                              # (80, 513) float32 weights
