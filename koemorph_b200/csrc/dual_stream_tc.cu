@@ -5,18 +5,26 @@
 //
 //   phase  MMA (M=128, cta_group::1, kind::f16)                         accumulator (TMEM columns)
 //   G1     z[tok 128(80) x 256]   = Xn[tok x 272] . Wc[256 x 272]^T      [0,256)
-//   S      s[hq 128 x tok 80]     = Qk_t[128 x 256] . enc[80 x 256]^T    [256,336) [336,416)   2 tiles of 4 heads
 //   VT     vT[d 128 x tok 80]     = Wv_t[128 x 256] . enc[80 x 256]^T    [0,80) [80,160)       2 tiles
+//   S      s[hq 128 x tok 80]     = Qk_t[128 x 256] . enc[80 x 256]^T    [256,336) [336,416)   2 tiles of 4 heads
 //   PV     o[hq 128 x d 128]      = P_t[128 x 80] . vT_t[128 x 80]^T     [160,288) [288,416)   (diagonal 32x32 blocks used)
-//   H1     h[q 128(28) x 128]     = O[q x 256] . Wa[128 x 256]^T         [0,128)
+//   H1     h[q 128(28) x 128]     = O[q x 256] . Wa[128 x 256]^T         [288,416)
 //
 // Operands live in shared memory in the canonical UMMA *no-swizzle K-major* layout: 8-row x 16-byte core
-// matrices, element (r, k) at (r/8)*SBO + (k/8)*128 + (r%8)*16 + (k%8)*2 bytes.  Activations are written in that
-// layout by the epilogue threads; weights are pre-tiled on the host into the same layout, 16 KiB per pipeline
-// stage, so the producer moves one stage with a single cp.async.bulk (TMA bulk copy) that completes on an
-// mbarrier.  Roles: warps 0-3 = SIMT (operand staging, TMEM epilogues; thread t owns TMEM lane t), warp 4 = TMA
-// producer, warp 5 = TMEM allocator + single-thread MMA issuer.  Phases are serialised by two mbarriers
-// (mma_go: 128 SIMT arrivals; mma_done: tcgen05.commit); the weight ring runs ahead across phases and windows.
+// matrices, element (r, k) at (r/8)*SBO + (k/8)*128 + (r%8)*16 + (k%8)*2 bytes (measured at the M=128 floor of
+// tcgen05.mma, scripts/microbench/umma_operand_layout_rate.cu).  Activations are written in that layout by the
+// epilogue threads; weights are pre-tiled on the host into the same layout, 16 KiB per pipeline stage, so a producer
+// moves one stage with a single cp.async.bulk (TMA bulk copy) that completes on an mbarrier.
+//
+// Roles (352 threads): warps 0-7 = SIMT (operand staging, TMEM epilogues; warps w and w + 4 own TMEM lanes
+// 32 (w % 4) .. +31 and split every epilogue), warp 8 = weight producer (ring slots 0-3), warp 9 = TMEM allocator +
+// MMA issuer (the whole warp runs the loop, one elected lane issues), warp 10 = mel-row producer (ring slots 4-5).
+// Phases are serialised by mbarriers (mma_go: 256 SIMT arrivals; mma_done / vt_done: tcgen05.commit); both rings
+// run ahead across phases and windows.  At 30 fps a window's timeline is
+//   G1(i) [under the decoder tail of i-1] -> LayerNorm -> VT, S GEMMs [SIMT: stage window i+1, then the vT epilogue]
+//   -> softmax -> PV -> O -> H1 -> decoder tail [G1(i+1) already running]
+// (DESIGN.md section 4 has the measured cycle counts); at 60 fps the first GEMM's operand spans the region the S/VT
+// GEMMs read, so the next window is staged after the decoder tail instead.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
