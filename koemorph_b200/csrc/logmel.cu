@@ -20,7 +20,11 @@
 //     and the control flow is warp-uniform.
 //   * results leave through a shared staging tile as coalesced rows of 80 mel values in dB.
 //   * the audio of the NEXT iteration is loaded into registers before the filterbank phase, so DRAM latency
-//     hides behind it.
+//     hides behind it -- also for the frame pairs that touch the padding / a window edge / the end of the clip
+//     (masked or reflected loads), which the launch order groups into 16-warp iterations of their own: a masked
+//     pair costs its warp ~25 % more instructions, and one such warp per iteration held 15 others at the barrier.
+//   * the default bank (sr 16000, 80 mels, 80..8000 Hz) runs the filterbank as straight-line FFMAs with immediate
+//     weights unrolled from compile-time tables (melbank_default.inc); any other bank takes the looped variant.
 #include <algorithm>
 #include <cmath>
 #include <mutex>
