@@ -150,7 +150,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 break
-            time.sleep(0.0005)
+            time.sleep(0.001)
 
     def start(self):
         if self._nv is not None:
