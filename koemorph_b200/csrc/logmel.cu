@@ -74,6 +74,9 @@ struct LogmelParams {
   float* frame_max_b;
   long long power_b_clip_stride, fmax_b_clip_stride;
   int edge_lo, edge_hi;          // leading / trailing frame pairs of a clip that need masked loads (launch order only)
+  int mid_pairs;                 // interior pairs per clip (0: no edge grouping, every pair is located the slow way)
+  int step_clips, step_pairs;    // gridDim.x * kWarps pairs, as whole clips of mid_pairs + a remainder
+  int store_order;               // 2 bits per warp class (warp / 4): where its store phase sits (see the kernel)
 };
 
 __host__ __device__ constexpr int bitrev5(int i) {
@@ -332,8 +335,43 @@ __device__ __forceinline__ void mel_phase_generic(int g, int gend, const int4* s
   }
 }
 
+// ---- mbarrier (shared-memory barrier object): arrive now, wait later -----------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded spin: a protocol bug traps (error to the host) instead of hanging the GPU
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && spin > (1u << 22)) __trap();
+  }
+}
+
 // kSplitB: the pairs' second frames go to their own buffer (LogmelParams::power_b; the streaming step) -- a separate
 // instantiation so that the batch kernel carries none of it (the extra pointer arithmetic cost it 3 us of 179)
+//
+// Schedule of one iteration (16 frame pairs per CTA, one per warp):
+//   F  window, first 32-point FFT, twiddles                          registers only
+//   W  wait "mel phase of the previous iteration done" (mbarrier): nobody reads this warp's tile any more
+//   T  transposition through the tile, second FFT, separation -> the pair's two power spectra in the tile
+//   L  the next pair's audio -> registers (in flight during everything below)
+//   B  __syncthreads: all 32 spectra of the iteration are in the tiles
+//   M  mel phase: lane = frame, warp = run of bins -> mel tile [iteration parity]; arrive on the mbarrier
+//   S  store phase of the PREVIOUS iteration's rows (the mel tiles are double buffered), placed per warp class
+//      (warp / 4, one warp of every class on each scheduler) either before F, between T and L, or after L: the classes
+//      then run the FFT a store phase apart, so that the FMA-bound and the shared-memory-bound stretches of different
+//      warps overlap instead of all 16 warps queueing for the same pipe at the same time.
 template <bool kDefaultBank, bool kSplitB = false>
 __global__ void __launch_bounds__(kThreads, 1)
 logmel_power_kernel(FrontendTables tab, LogmelParams p) {
@@ -343,9 +381,9 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   float2* s_binw = s_tw + 1024;                                    // kMaxBins float2
   int4* s_groups = reinterpret_cast<int4*>(s_binw + kMaxBins);     // kMaxGroups
   int* s_runs = reinterpret_cast<int*>(s_groups + kMaxGroups);     // kWarps + 1 (+ pad to 32)
-  float* s_tlo = reinterpret_cast<float*>(s_runs + 32);            // kSlots * kTileStride: falling halves (filter g of group g)
-  float* s_thi = s_tlo + kSlots * kTileStride;                     // kSlots * kTileStride: rising halves (filter g + 1)
-  float* s_scratch = s_thi + kSlots * kTileStride;                 // kWarps * kScratch, 16-byte aligned, bank 0
+  float* s_tiles = reinterpret_cast<float*>(s_runs + 32);          // 2 buffers x (tlo | thi), each kSlots * kTileStride
+  float* s_scratch = s_tiles + 4 * kSlots * kTileStride;           // kWarps * kScratch, 16-byte aligned, bank 0
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scratch + kWarps * kScratch);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // the next kernel of the stream (the emotion stream, which reads nothing this kernel writes) may take each SM as soon
@@ -358,7 +396,12 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   for (int i = tid; i < tab.n_groups; i += kThreads) s_groups[i] = tab.groups[i];
   if (tid <= kWarps) s_runs[tid] = tab.runs[tid];
   // cells that no group writes (filter 0's rising half; filters without a falling / rising group in sparse banks) stay 0
-  for (int i = tid; i < 2 * kSlots * kTileStride; i += kThreads) s_tlo[i] = 0.0f;
+  for (int i = tid; i < 4 * kSlots * kTileStride; i += kThreads) s_tiles[i] = 0.0f;
+  const uint32_t mel_done = smem_addr(s_bar);
+  if (tid == 0) {
+    bar_init(mel_done, kWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
   const unsigned ppc = (unsigned)(p.n_frames + 1) >> 1;  // frame pairs per clip
@@ -366,14 +409,97 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   const unsigned n_iters = (total_pairs + kWarps - 1) / kWarps;
   float* xb = s_scratch + warp * kScratch;
   float2* xb2 = reinterpret_cast<float2*>(xb);
+  const int order = (p.store_order >> (2 * (warp >> 2))) & 3;  // 0: S before F; 1: S after L; 2: S between T and L
+
+  // store phase of one frame pair: warp w owns slots 2w, 2w+1 of the mel tiles
+  auto store_rows = [&](int clip, int frame, bool has_b, const float* tiles) {
+      const float* tlo = tiles + (2 * warp) * kTileStride;
+      const float* thi = tlo + kSlots * kTileStride;
+      float* dst = p.power + (long long)clip * p.power_clip_stride + (long long)frame * KOE_N_MELS;
+      // the 160 values of the two rows (row B follows row A in the clip's block), five per lane: j = lane + 32 q;
+      // j < 80 -> frame A filter j, else frame B filter j - 80, which sits kTileStride - 80 = 1 float further in the tile
+      float db[5];
+#pragma unroll
+      for (int qd = 0; qd < 5; ++qd) {
+        const int j = lane + 32 * qd;
+        const bool second = qd > 2 || (qd == 2 && lane >= KOE_N_MELS - 64);
+        const int t = j + (second ? kTileStride - KOE_N_MELS : 0);
+        const float pw = tlo[t] + thi[t];
+        // stored in dB (the consumer only subtracts its reference and clamps), or as ln(p + eps) for the torchaudio flavour
+        db[qd] = tab.log_mode == 0 ? db_from_power(pw) : ln_from_power(pw, tab.log_eps);
+      }
+      float mx_a = fmaxf(db[0], db[1]), mx_b = fmaxf(db[3], db[4]);
+      if (lane < KOE_N_MELS - 64) mx_a = fmaxf(mx_a, db[2]); else mx_b = fmaxf(mx_b, db[2]);
+      // row B follows row A, or goes to its own buffer (power_b: pair j of the clip -> row j there); dst_b is biased by
+      // one row so that the same indices address it
+      float* dst_b = dst;
+      if constexpr (kSplitB)
+        dst_b = p.power_b + (long long)clip * p.power_b_clip_stride + (long long)(frame >> 1) * KOE_N_MELS - KOE_N_MELS;
+      dst[lane] = db[0];
+      dst[lane + 32] = db[1];
+      float* dst_mid = lane < KOE_N_MELS - 64 ? dst : dst_b;  // the third 32-value piece straddles the two rows
+      if (has_b || lane < KOE_N_MELS - 64) dst_mid[lane + 64] = db[2];
+      if (has_b) {
+        dst_b[lane + 96] = db[3];
+        dst_b[lane + 128] = db[4];
+      }
+      if (p.frame_max != nullptr) {
+        const int ia = __reduce_max_sync(kFullMask, float_order(mx_a));
+        const int ib = __reduce_max_sync(kFullMask, float_order(mx_b));
+        float* fm = p.frame_max + (long long)clip * p.fmax_clip_stride + frame;
+        float* fm_b = fm;
+        if constexpr (kSplitB) fm_b = p.frame_max_b + (long long)clip * p.fmax_b_clip_stride + (frame >> 1) - 1;
+        if (lane == 0) fm[0] = order_float(ia);
+        if (lane == 1 && has_b) fm_b[1] = order_float(ib);
+      }
+  };
+
+  // Pair of iteration `it` for this warp.  Interior pairs (all but the few per clip that touch an edge) come last in the
+  // launch order, clip by clip; their position advances by a constant number of pairs per iteration, so clip and pair
+  // are kept incrementally (no division in the loop).
+  const unsigned n_edge_pairs = p.mid_pairs > 0 ? (unsigned)p.n_clips * (unsigned)(p.edge_lo + p.edge_hi) : total_pairs;
+  int in_clip = -1, in_j = 0;  // interior position of the pair located last (-1: none yet)
+  auto locate = [&](unsigned iter) -> PairInfo {
+    const unsigned pair = iter < n_iters ? iter * kWarps + warp : total_pairs;
+    if (pair < n_edge_pairs || pair >= total_pairs) {
+      in_clip = -1;
+      return locate_pair(p, pair, total_pairs, ppc);
+    }
+    if (in_clip < 0) {
+      const unsigned r = pair - n_edge_pairs;
+      in_clip = (int)(r / (unsigned)p.mid_pairs);
+      in_j = (int)(r - (unsigned)in_clip * (unsigned)p.mid_pairs);
+    } else {
+      in_clip += p.step_clips;
+      in_j += p.step_pairs;
+      if (in_j >= p.mid_pairs) in_j -= p.mid_pairs, ++in_clip;
+    }
+    PairInfo pi;
+    pi.clip = in_clip;
+    pi.frame = 2 * (p.edge_lo + in_j);
+    pi.has_b = true;
+    pi.interior = true;
+    pi.fa_lo = p.sample_offset + (p.frame_offset + pi.frame * p.frame_step) * p.hop - kFrameLen / 2;
+    pi.fb_lo = pi.fa_lo + p.frame_step * p.hop;
+    return pi;
+  };
 
   float2 v[32];
   unsigned it = blockIdx.x;
-  PairInfo nxt = locate_pair(p, it < n_iters ? it * kWarps + warp : total_pairs, total_pairs, ppc);
+  PairInfo nxt = locate(it);
   if (nxt.interior) load_interior(p, nxt, lane, v);
   else if (nxt.frame >= 0) load_edge(p, nxt, lane, v);
+  int pend_clip = 0, pend_frame = -1;  // the pair whose mel rows wait in the tiles for their store phase
+  bool pend_has_b = false;
+  unsigned k = 0;                      // iterations done by this CTA: parity of the mbarrier phase / tile buffer
 
-  for (; it < n_iters; it += gridDim.x) {
+  for (; it < n_iters; it += gridDim.x, ++k) {
+    const float* prev_tiles = s_tiles + ((k + 1) & 1) * (2 * kSlots * kTileStride);
+    if (order == 0 && pend_frame >= 0) {
+      bar_wait(mel_done, (k + 1) & 1);  // the previous mel phase, by every warp
+      store_rows(pend_clip, pend_frame, pend_has_b, prev_tiles);
+      pend_frame = -1;
+    }
     // ------------------------------------------------------------------ FFT phase (per warp)
     const PairInfo cur = nxt;
     if (cur.frame >= 0) {
@@ -387,6 +513,10 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
         float2 r = __fmul2_rn(z, bcast(w.x));
         v[k1] = __ffma2_rn(make_float2(-z.y, z.x), bcast(w.y), r);
       }
+    }
+    // the tile still holds this warp's spectra of the previous iteration until every warp has finished that mel phase
+    if (k > 0) bar_wait(mel_done, (k + 1) & 1);
+    if (cur.frame >= 0) {
       // 32x32 transpose of complex values through the warp's padded tile
 #pragma unroll
       for (int k1 = 0; k1 < 32; ++k1) xb2[k1 * kRowF2 + lane] = v[k1];
@@ -431,71 +561,43 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
         pb[512] = 4.0f * v[16].y * v[16].y;
       }
     }
-    // audio of the next iteration: in flight during the filterbank / store phases
-    nxt = locate_pair(p, it + gridDim.x < n_iters ? (it + gridDim.x) * kWarps + warp : total_pairs, total_pairs, ppc);
+    if (order == 2 && pend_frame >= 0) {
+      store_rows(pend_clip, pend_frame, pend_has_b, prev_tiles);
+      pend_frame = -1;
+    }
+    // audio of the next iteration: in flight during the mel / store phases
+    nxt = locate(it + gridDim.x);
     if (nxt.interior) load_interior(p, nxt, lane, v);
     else if (nxt.frame >= 0) load_edge(p, nxt, lane, v);
+    if (order == 1 && pend_frame >= 0) {
+      store_rows(pend_clip, pend_frame, pend_has_b, prev_tiles);
+      pend_frame = -1;
+    }
     __syncthreads();
 
     // ------------------------------------------------------------------ mel phase: lane = frame slot, warp = run of bins
     {
+      float* tlo = s_tiles + (k & 1) * (2 * kSlots * kTileStride) + lane * kTileStride;
+      float* thi = tlo + kSlots * kTileStride;
       const float* spec = s_scratch + (lane >> 1) * kScratch + (lane & 1) * kSecondFrame;
       if (kDefaultBank)
-        mel_phase_default(warp, spec, s_tlo + lane * kTileStride, s_thi + lane * kTileStride);
+        mel_phase_default(warp, spec, tlo, thi);
       else
-        mel_phase_generic(s_runs[warp], s_runs[warp + 1], s_groups, s_binw, spec, s_tlo + lane * kTileStride,
-                          s_thi + lane * kTileStride);
+        mel_phase_generic(s_runs[warp], s_runs[warp + 1], s_groups, s_binw, spec, tlo, thi);
     }
-    __syncthreads();
-
-    // ------------------------------------------------------------------ store phase: warp w owns slots 2w, 2w+1
-    if (cur.frame >= 0) {
-      const float* tlo = s_tlo + (2 * warp) * kTileStride;
-      const float* thi = s_thi + (2 * warp) * kTileStride;
-      float* dst = p.power + (long long)cur.clip * p.power_clip_stride + (long long)cur.frame * KOE_N_MELS;
-      // the 160 values of the two rows (row B follows row A in the clip's block), five per lane: j = lane + 32 q;
-      // j < 80 -> frame A filter j, else frame B filter j - 80, which sits kTileStride - 80 = 1 float further in the tile
-      float db[5];
-#pragma unroll
-      for (int qd = 0; qd < 5; ++qd) {
-        const int j = lane + 32 * qd;
-        const bool second = qd > 2 || (qd == 2 && lane >= KOE_N_MELS - 64);
-        const int t = j + (second ? kTileStride - KOE_N_MELS : 0);
-        const float pw = tlo[t] + thi[t];
-        // stored in dB (the consumer only subtracts its reference and clamps), or as ln(p + eps) for the torchaudio flavour
-        db[qd] = tab.log_mode == 0 ? db_from_power(pw) : ln_from_power(pw, tab.log_eps);
-      }
-      float mx_a = fmaxf(db[0], db[1]), mx_b = fmaxf(db[3], db[4]);
-      if (lane < KOE_N_MELS - 64) mx_a = fmaxf(mx_a, db[2]); else mx_b = fmaxf(mx_b, db[2]);
-      // row B follows row A, or goes to its own buffer (power_b: pair j of the clip -> row j there); dst_b is biased by
-      // one row so that the same indices address it
-      float* dst_b = dst;
-      if constexpr (kSplitB)
-        dst_b = p.power_b + (long long)cur.clip * p.power_b_clip_stride + (long long)(cur.frame >> 1) * KOE_N_MELS - KOE_N_MELS;
-      dst[lane] = db[0];
-      dst[lane + 32] = db[1];
-      float* dst_mid = lane < KOE_N_MELS - 64 ? dst : dst_b;  // the third 32-value piece straddles the two rows
-      if (cur.has_b || lane < KOE_N_MELS - 64) dst_mid[lane + 64] = db[2];
-      if (cur.has_b) {
-        dst_b[lane + 96] = db[3];
-        dst_b[lane + 128] = db[4];
-      }
-      if (p.frame_max != nullptr) {
-        const int ia = __reduce_max_sync(kFullMask, float_order(mx_a));
-        const int ib = __reduce_max_sync(kFullMask, float_order(mx_b));
-        float* fm = p.frame_max + (long long)cur.clip * p.fmax_clip_stride + cur.frame;
-        float* fm_b = fm;
-        if constexpr (kSplitB) fm_b = p.frame_max_b + (long long)cur.clip * p.fmax_b_clip_stride + (cur.frame >> 1) - 1;
-        if (lane == 0) fm[0] = order_float(ia);
-        if (lane == 1 && cur.has_b) fm_b[1] = order_float(ib);
-      }
-    }
+    __syncwarp();
+    if (lane == 0) bar_arrive(mel_done);
+    pend_clip = cur.clip, pend_frame = cur.frame, pend_has_b = cur.has_b;
+  }
+  if (pend_frame >= 0) {
+    bar_wait(mel_done, (k + 1) & 1);
+    store_rows(pend_clip, pend_frame, pend_has_b, s_tiles + ((k + 1) & 1) * (2 * kSlots * kTileStride));
   }
 }
 
 constexpr size_t kLogmelSmem = sizeof(float) * kFrameLen + sizeof(float2) * 1024 + sizeof(float2) * kMaxBins +
                                sizeof(int4) * kMaxGroups + sizeof(int) * 32 +
-                               sizeof(float) * (2 * kSlots * kTileStride + kWarps * kScratch);
+                               sizeof(float) * (4 * kSlots * kTileStride + kWarps * kScratch) + 16;
 
 // ---- dB normalisation: ref = clip max, clamp, rescale; emits long-term and last-3 short-term features
 __global__ void logmel_normalise_kernel(const float* __restrict__ power, const float* __restrict__ frame_max,
@@ -826,6 +928,13 @@ extern "C" int koe_frontend_filterbank_host(const koe_frontend_t* fe, float* fb_
   return KOE_OK;
 }
 
+// experiment switch of the log-mel kernel (scripts/k1_variants.py): placement of the store phase per warp class
+static int g_k1_store_order = 0x44;  // classes 0, 2: before the FFT; classes 1, 3: after the next pair's loads
+extern "C" int koe_debug_k1_variant(int store_order) {
+  g_k1_store_order = store_order;
+  return KOE_OK;
+}
+
 extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_args* a, void* stream) {
   KOE_REQUIRE(fe != nullptr && a != nullptr && a->audio != nullptr && a->power != nullptr,
               "koe_logmel_power: NULL argument");
@@ -891,6 +1000,14 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
   const long long n_blocks = ((long long)a->n_clips * ppc + kWarps - 1) / kWarps;
   const long long max_grid = (long long)fe->num_sms * fe->occupancy;
   const int grid = (int)std::min(n_blocks, max_grid);
+  p.store_order = g_k1_store_order;
+  p.mid_pairs = 0, p.step_clips = 0, p.step_pairs = 0;
+  if (p.edge_lo + p.edge_hi > 0 && p.edge_lo + p.edge_hi < (int)ppc) {
+    p.mid_pairs = (int)ppc - p.edge_lo - p.edge_hi;
+    const long long step = (long long)grid * kWarps;
+    p.step_clips = (int)(step / p.mid_pairs);
+    p.step_pairs = (int)(step % p.mid_pairs);
+  }
   if (p.power_b != nullptr) {
     if (fe->default_bank)
       logmel_power_kernel<true, true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
