@@ -42,7 +42,7 @@ extern "C" {
 const char* koe_last_error(void);
 int koe_version(void);
 /* sizeof of the public argument structs, for bindings that mirror them (ctypes, cgo, JNI): 0 koe_frontend_config,
- * 1 koe_logmel_args, 2 koe_core_weights, 3 koe_stream_args; -1 for any other index */
+ * 1 koe_logmel_args, 2 koe_core_weights, 3 koe_stream_args, 4 koe_forward_args; -1 for any other index */
 int koe_sizeof_struct(int which);
 /* number of kernels launched by this library in this process since load / since the last reset */
 int64_t koe_launch_count(void);
@@ -203,6 +203,14 @@ int koe_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_cli
                        void* stream);
 
 /*
+ * y[r] = x[r] . w_t + b for n_rows rows: the stand-alone form of the 264 -> 256 eGeMAPS compression
+ * (get_concatenated_features, src/features/opensmile_extractor.py:583-604), which SimplifiedDualStreamModel
+ * .extract_emotion_features returns.  w_t is [n_in][n_out] (the nn.Linear weight transposed), row-major float32.
+ */
+int koe_affine_rows(const float* x, int n_rows, int n_in, const float* w_t, const float* b, int n_out, float* y,
+                    void* stream);
+
+/*
  * Windows of mel power -> blendshape frames.  Output frame i of clip b uses the window whose first frame
  * is g0 = i*stride_frames and that holds frames_per_window (T) frames; its frame k comes from
  *   power[1 + 2*k]       row (b, i)        lo-edge variant k      if k <  n_edge
@@ -217,7 +225,7 @@ int koe_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_cli
  *   out           [n_clips][n_out][52]  final blendshapes (before temporal smoothing)
  *   sigmoid_out   [n_clips][n_out][52]  decoder output before the stream-weight fusion, or NULL
  *   attn_out      [n_clips][n_out][28][80] head-averaged mel attention weights, or NULL
- * precision: 0 = fp32 CUDA-core FMA; 1 = tf32 tcgen05; 2 = bf16 tcgen05.
+ * precision: 0 = fp32 CUDA-core FMA; 2 = bf16 operands on tcgen05 with fp32 accumulation (1 is reserved and rejected).
  */
 int koe_dual_stream_windows(const koe_core_weights* w, const float* const* power, const float* const* frame_max,
                             int n_edge, int n_clips, int n_frames, int n_out, int stride_frames,
@@ -276,6 +284,38 @@ typedef struct {
   int64_t step;
 } koe_stream_args;
 int koe_stream_push(const koe_stream_args* args, int* emitted, void* stream);
+
+/*
+ * The whole forward of SequentialDualStreamModel.forward (src/model/sequential_dual_stream_model.py:63-167) -- or, with
+ * n_out = 1 and n_edge = 0, of SimplifiedDualStreamModel.forward (src/model/simplified_dual_stream_model.py:370-415) --
+ * as ONE call: koe_logmel_power on the clip's global frames, the 2 * n_edge edge-variant launches on the window grid,
+ * koe_emotion_stream, koe_dual_stream_windows and (smooth != 0, n_out > 1) koe_ema_scan, queued back to back on `stream`.
+ * Because the call knows which kernel precedes which, the emotion stream and the core are chained to the frontend with
+ * programmatic dependent launch (they start on SMs the frontend's last CTAs have left); the public single-kernel entries
+ * above keep plain stream order.  Window i of a clip starts at global frame i * stride_frames and holds
+ * frames_per_window frames; n_frames >= (n_out - 1) * stride_frames + frames_per_window global frames are computed.
+ * Workspace (caller-owned): power[0] / frame_max[0] [n_clips][n_frames][80] / [n_clips][n_frames]; for m < n_edge
+ * power[1 + 2m], power[2 + 2m] [n_clips][n_out][80] (+ frame_max); expr_sigmoid [n_clips].
+ */
+typedef struct {
+  const koe_frontend_t* frontend;
+  const koe_core_weights* weights;
+  const float* audio;      /* [n_clips][audio_stride] */
+  int64_t audio_stride;
+  int32_t n_clips, n_samples, hop;
+  int32_t n_frames, frames_per_window, stride_frames, n_out, n_edge;
+  const float* egemaps;    /* [n_clips][weights->emo_in] */
+  float* power[1 + 2 * KOE_MAX_EDGE];
+  float* frame_max[1 + 2 * KOE_MAX_EDGE];
+  float* expr_sigmoid;
+  float* out;              /* [n_clips][n_out][52] */
+  float* sigmoid_out;      /* or NULL */
+  float* attn_out;         /* or NULL */
+  float alpha;             /* sigmoid(smoothing_alpha) */
+  int32_t smooth;          /* != 0: EMA over the n_out frames of every clip (first frame passes through) */
+  int32_t precision;
+} koe_forward_args;
+int koe_forward_windows(const koe_forward_args* args, void* stream);
 
 /*
  * Learnable-alpha exponential smoothing along the frame axis, in place

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libkoemorph_b200.so")
 
 KOE_NO_EDGE = -1000000
 MAX_EDGE = 2
-PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
+# 1 was reserved for a tf32 tensor-core core that was never built: the ABI rejects it
+PRECISIONS = {"fp32": 0, "bf16": 2}
 
 
 class CoreWeightsStruct(C.Structure):
@@ -60,6 +61,18 @@ class StreamArgs(C.Structure):
                 ("step", C.c_int64)]
 
 
+class ForwardArgs(C.Structure):
+    """koe_forward_args (include/koemorph_b200.h)."""
+    _fields_ = [("frontend", C.c_void_p), ("weights", C.c_void_p), ("audio", C.c_void_p), ("audio_stride", C.c_int64),
+                ("n_clips", C.c_int32), ("n_samples", C.c_int32), ("hop", C.c_int32),
+                ("n_frames", C.c_int32), ("frames_per_window", C.c_int32), ("stride_frames", C.c_int32),
+                ("n_out", C.c_int32), ("n_edge", C.c_int32),
+                ("egemaps", C.c_void_p), ("power", C.c_void_p * (1 + 2 * MAX_EDGE)),
+                ("frame_max", C.c_void_p * (1 + 2 * MAX_EDGE)), ("expr_sigmoid", C.c_void_p), ("out", C.c_void_p),
+                ("sigmoid_out", C.c_void_p), ("attn_out", C.c_void_p), ("alpha", C.c_float), ("smooth", C.c_int32),
+                ("precision", C.c_int32)]
+
+
 class FrontendConfig(C.Structure):
     """koe_frontend_config (include/koemorph_b200.h)."""
     _fields_ = [("device", C.c_int32), ("sample_rate", C.c_int32), ("n_fft", C.c_int32), ("n_mels", C.c_int32),
@@ -92,6 +105,8 @@ _SIGNATURES = {
     "koe_pcm16_to_float": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "koe_sizeof_struct": (C.c_int, [C.c_int]),
     "koe_stream_push": (C.c_int, [C.POINTER(StreamArgs), C.POINTER(C.c_int), C.c_void_p]),
+    "koe_forward_windows": (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p]),
+    "koe_affine_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "koe_emotion_stream": (C.c_int, [C.POINTER(CoreWeightsStruct), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "koe_dual_stream_windows": (C.c_int, [C.POINTER(CoreWeightsStruct), C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -11,6 +11,7 @@ extern "C" int koe_sizeof_struct(int which) {
     case 1: return (int)sizeof(koe_logmel_args);
     case 2: return (int)sizeof(koe_core_weights);
     case 3: return (int)sizeof(koe_stream_args);
+    case 4: return (int)sizeof(koe_forward_args);
     default: return -1;
   }
 }

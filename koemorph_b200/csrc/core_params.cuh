@@ -35,4 +35,8 @@ __device__ __forceinline__ long long window_row(const CoreParams& p, int variant
                       : (long long)b * p.n_out + wi;
 }
 
+// emotion stream launch shared by the public entry and the fused forward (csrc/session.cu); see dual_stream.cu
+int launch_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid, void* stream,
+                          bool after_frontend);
+
 }  // namespace koe

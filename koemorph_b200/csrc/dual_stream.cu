@@ -608,8 +608,11 @@ static int validate_weights(const koe_core_weights* w) {
   return KOE_OK;
 }
 
-extern "C" int koe_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid,
-                                  void* stream) {
+// `after_frontend`: the caller guarantees that the kernel queued just before this one on `stream` is the log-mel frontend,
+// which writes nothing this kernel reads -- only then may it start beside that kernel's last CTAs (programmatic dependent
+// launch).  From the public entry the producer of emo_in may be the previous kernel, so that launch keeps full stream order.
+int koe::launch_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid,
+                               void* stream, bool after_frontend) {
   if (int rc = validate_weights(w)) return rc;
   KOE_REQUIRE(emo_in != nullptr && expr_sigmoid != nullptr && n_clips >= 0, "koe_emotion_stream: bad argument");
   if (n_clips == 0) return KOE_OK;
@@ -623,12 +626,55 @@ extern "C" int koe_emotion_stream(const koe_core_weights* w, const float* emo_in
     configured[dev] = true;
   }
   // every CTA streams all the weights (0.4 MB, L2 resident): few clips per CTA while that keeps the grid within ~4 waves
-  if (n_clips <= 4 * 600)
-    KOE_CUDA(launch_after_primary_starts(emotion_stream_kernel<4>, dim3((n_clips + 3) / 4), dim3(256), kEmoSmem,
-                                         (cudaStream_t)stream, *w, emo_in, n_clips, expr_sigmoid));
-  else
-    KOE_CUDA(launch_after_primary_starts(emotion_stream_kernel<16>, dim3((n_clips + 15) / 16), dim3(256), kEmoSmem,
-                                         (cudaStream_t)stream, *w, emo_in, n_clips, expr_sigmoid));
+  const bool small = n_clips <= 4 * 600;
+  const dim3 grid(small ? (n_clips + 3) / 4 : (n_clips + 15) / 16);
+  if (after_frontend) {
+    if (small)
+      KOE_CUDA(launch_after_primary_starts(emotion_stream_kernel<4>, grid, dim3(256), kEmoSmem, (cudaStream_t)stream, *w,
+                                           emo_in, n_clips, expr_sigmoid));
+    else
+      KOE_CUDA(launch_after_primary_starts(emotion_stream_kernel<16>, grid, dim3(256), kEmoSmem, (cudaStream_t)stream, *w,
+                                           emo_in, n_clips, expr_sigmoid));
+  } else if (small) {
+    emotion_stream_kernel<4><<<grid, 256, kEmoSmem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
+  } else {
+    emotion_stream_kernel<16><<<grid, 256, kEmoSmem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
+  }
+  count_launch();
+  KOE_CUDA(cudaGetLastError());
+  return KOE_OK;
+}
+
+extern "C" int koe_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid,
+                                  void* stream) {
+  return koe::launch_emotion_stream(w, emo_in, n_clips, expr_sigmoid, stream, /*after_frontend=*/false);
+}
+
+// ---- y = x W^T + b for a handful of rows: the 264 -> 256 eGeMAPS compression as a stand-alone call
+// (OpenSMILEeGeMAPSExtractor.get_concatenated_features, src/features/opensmile_extractor.py:583-604; the batch path folds
+// this layer into the emotion stream instead)
+namespace koe {
+__global__ void __launch_bounds__(256) affine_rows_kernel(const float* __restrict__ x, int n_in,
+                                                          const float* __restrict__ w_t, const float* __restrict__ b,
+                                                          int n_out, float* __restrict__ y) {
+  extern __shared__ float s_x[];
+  const int r = blockIdx.x;
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) s_x[i] = x[(long long)r * n_in + i];
+  __syncthreads();
+  for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+    float acc = 0.0f;
+    for (int i = 0; i < n_in; ++i) acc = fmaf(s_x[i], w_t[(long long)i * n_out + o], acc);
+    y[(long long)r * n_out + o] = acc + b[o];
+  }
+}
+}  // namespace koe
+
+extern "C" int koe_affine_rows(const float* x, int n_rows, int n_in, const float* w_t, const float* b, int n_out, float* y,
+                               void* stream) {
+  KOE_REQUIRE(n_rows >= 0 && n_in > 0 && n_in <= 8192 && n_out > 0, "koe_affine_rows: bad sizes");
+  if (n_rows == 0) return KOE_OK;
+  KOE_REQUIRE(x && w_t && b && y, "koe_affine_rows: NULL argument");
+  koe::affine_rows_kernel<<<n_rows, 256, n_in * sizeof(float), (cudaStream_t)stream>>>(x, n_in, w_t, b, n_out, y);
   count_launch();
   KOE_CUDA(cudaGetLastError());
   return KOE_OK;
@@ -661,8 +707,8 @@ static int launch_core(const CoreParams& p_in, int precision, cudaStream_t strea
     KOE_CUDA(cudaGetLastError());
     return KOE_OK;
   }
-  if (precision == 1 || precision == 2) return launch_dual_stream_tc(p, precision, stream);
-  return fail(KOE_E_INVALID, "precision must be 0 (fp32), 1 (tf32) or 2 (bf16), got %d", precision);
+  if (precision == 2) return launch_dual_stream_tc(p, precision, stream);
+  return fail(KOE_E_INVALID, "precision must be 0 (fp32) or 2 (bf16 operands, tcgen05), got %d", precision);
 }
 
 extern "C" int koe_dual_stream_windows(const koe_core_weights* w, const float* const* power,

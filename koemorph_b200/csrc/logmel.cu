@@ -573,6 +573,10 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
       store_rows(pend_clip, pend_frame, pend_has_b, prev_tiles);
       pend_frame = -1;
     }
+    if (p.store_order & 0x100) {  // timing probe (scripts/k1_variants.py): FFT + loads only, free running, no results
+      if (lane == 0) bar_arrive(mel_done);
+      continue;
+    }
     __syncthreads();
 
     // ------------------------------------------------------------------ mel phase: lane = frame slot, warp = run of bins

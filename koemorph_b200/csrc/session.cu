@@ -9,7 +9,7 @@
 // mel rows with their per-frame maxima, one "window ends here" row (L), the smoothing state.  SURVEY.md section 8
 // note E: frame n is centred on sample n * hop; R[n] is the same frame with everything before its centre zeroed; L[n + 1]
 // is centred on (n + 1) * hop with everything from there on zeroed.
-#include "common.cuh"
+#include "core_params.cuh"
 
 namespace koe {
 
@@ -48,7 +48,10 @@ extern "C" int koe_stream_push(const koe_stream_args* a, int* emitted, void* str
   const float* old_tail = a->tail[n & 1];
   float* tail = a->tail[(n + 1) & 1];
   {
-    const int grid = std::min(S, 148 * 8);
+    int dev = 0, sms = 0;
+    KOE_CUDA(cudaGetDevice(&dev));
+    KOE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = std::min(S, sms * 8);
     stream_tail_shift_kernel<<<grid, 256, 0, stream>>>(old_tail, a->hop_audio, S, tail_len, hop, tail);
     count_launch();
     KOE_CUDA(cudaGetLastError());
@@ -91,5 +94,57 @@ extern "C" int koe_stream_push(const koe_stream_args* a, int* emitted, void* str
   if (a->ema_state != nullptr)
     if (int rc = koe_ema_scan(a->out, S, 1, a->alpha, a->ema_state, a->has_state, stream)) return rc;
   *emitted = 1;
+  return KOE_OK;
+}
+
+// ---- the batch forward as one native call (see koe_forward_windows in the header) ------------------------------------
+extern "C" int koe_forward_windows(const koe_forward_args* a, void* stream) {
+  KOE_REQUIRE(a != nullptr && a->frontend != nullptr && a->weights != nullptr, "koe_forward_windows: NULL argument");
+  KOE_REQUIRE(a->audio && a->egemaps && a->power[0] && a->frame_max[0] && a->expr_sigmoid && a->out,
+              "koe_forward_windows: NULL buffer");
+  KOE_REQUIRE(a->n_clips >= 0 && a->n_samples >= 0 && a->hop > 0 && a->n_out >= 1 && a->stride_frames >= 1 &&
+                  a->frames_per_window >= 1 && a->n_edge >= 0 && a->n_edge <= KOE_MAX_EDGE,
+              "koe_forward_windows: bad geometry");
+  KOE_REQUIRE((long long)(a->n_out - 1) * a->stride_frames + a->frames_per_window <= a->n_frames,
+              "koe_forward_windows: windows run past n_frames");
+  if (a->n_clips == 0) return KOE_OK;
+  koe_logmel_args f = {};
+  f.audio = a->audio;
+  f.audio_stride = a->audio_stride;
+  f.n_clips = a->n_clips;
+  f.n_samples = a->n_samples;
+  f.hop = a->hop;
+  f.pad_mode = 0;
+  f.sample_offset = 0;
+  // every global frame once
+  f.n_frames = a->n_frames;
+  f.frame_offset = 0, f.frame_step = 1;
+  f.lo_rel_hops = KOE_NO_EDGE, f.hi_rel_hops = KOE_NO_EDGE;
+  f.power = a->power[0], f.power_clip_stride = (int64_t)a->n_frames * KOE_N_MELS;
+  f.frame_max = a->frame_max[0], f.frame_max_clip_stride = a->n_frames;
+  if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+  // the frames within n_fft/2 of a window edge, once per window (SURVEY.md section 8 note E)
+  for (int m = 0; m < a->n_edge; ++m) {
+    KOE_REQUIRE(a->power[1 + 2 * m] && a->power[2 + 2 * m] && a->frame_max[1 + 2 * m] && a->frame_max[2 + 2 * m],
+                "koe_forward_windows: NULL edge buffer");
+    f.n_frames = a->n_out;
+    f.frame_step = a->stride_frames;
+    f.power_clip_stride = (int64_t)a->n_out * KOE_N_MELS, f.frame_max_clip_stride = a->n_out;
+    f.frame_offset = m, f.lo_rel_hops = -m, f.hi_rel_hops = KOE_NO_EDGE;
+    f.power = a->power[1 + 2 * m], f.frame_max = a->frame_max[1 + 2 * m];
+    if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+    f.frame_offset = a->frames_per_window - 1 - m, f.lo_rel_hops = KOE_NO_EDGE, f.hi_rel_hops = m;
+    f.power = a->power[2 + 2 * m], f.frame_max = a->frame_max[2 + 2 * m];
+    if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+  }
+  // the kernel queued last is a frontend launch: the emotion stream (which reads none of its outputs) may overlap its tail
+  if (int rc = launch_emotion_stream(a->weights, a->egemaps, a->n_clips, a->expr_sigmoid, stream, /*after_frontend=*/true))
+    return rc;
+  if (int rc = koe_dual_stream_windows(a->weights, a->power, a->frame_max, a->n_edge, a->n_clips, a->n_frames, a->n_out,
+                                       a->stride_frames, a->frames_per_window, a->expr_sigmoid, a->out, a->sigmoid_out,
+                                       a->attn_out, a->precision, stream))
+    return rc;
+  if (a->smooth && a->n_out > 1)
+    if (int rc = koe_ema_scan(a->out, a->n_clips, a->n_out, a->alpha, nullptr, 0, stream)) return rc;
   return KOE_OK;
 }

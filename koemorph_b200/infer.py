@@ -88,10 +88,17 @@ class HostPipeline:
         pcm = audio_host.dtype == torch.int16
         B, L = audio_host.shape
         eg = egemaps_host.reshape(B, 264)
-        n_out = self.model.num_output_frames(L) if hasattr(self.model, "num_output_frames") else None
-        shape = (B, n_out, 52) if n_out is not None else (B, 52)
+        model = self.model
+        sequential = hasattr(model, "num_output_frames")
+        n_out = model.num_output_frames(L) if sequential else None
+        shape = (B, n_out, 52) if sequential else (B, 52)
         if out_host is None:
             out_host = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        # every chunk runs the STATELESS part of the forward and writes its rows into one device buffer; the model's
+        # cross-call smoothing state is touched once, after the loop, on the caller's stream -- chunking must not change the
+        # result (SimplifiedDualStreamModel.forward blends a call with the previous call's output, and consecutive chunks
+        # hold different clips)
+        full = torch.empty(shape, dtype=torch.float32, device=self.device)
         cur = torch.cuda.current_stream(self.device)
         for s in self._streams:
             s.wait_stream(cur)
@@ -107,9 +114,15 @@ class HostPipeline:
                 else:
                     a_dev.copy_(audio_host[c0:c0 + n], non_blocking=True)
                 e_dev.copy_(eg[c0:c0 + n], non_blocking=True)
-                res = self.model(a_dev, egemaps=e_dev)["blendshapes"]
-                out_host[c0:c0 + n].copy_(res, non_blocking=True)
+                model._forward_frames(a_dev, e_dev, False, out=full[c0:c0 + n])
+                if sequential:
+                    out_host[c0:c0 + n].copy_(full[c0:c0 + n], non_blocking=True)
         for s in self._streams:
             cur.wait_stream(s)
+        if sequential:
+            # what SequentialDualStreamModel.forward leaves behind (reference :99,136): the last frame of every clip
+            model.prev_blendshapes = full[:, -1] if model.use_temporal_smoothing else None
+        else:
+            out_host.copy_(model.apply_temporal_smoothing(full), non_blocking=True)
         cur.synchronize()
         return out_host

@@ -95,3 +95,44 @@ class BlendshapeStreamer:
         if self._fh is not None:
             self._fh.close()
         self._sock = self._fh = None
+
+
+# ---- window slicing of a long recording (SequentialKoeMorphDataset._process_file_pair, sequential_dataset.py:157-206) ------
+def align_recording(n_samples: int, n_label_frames: int, hop_length: int) -> Tuple[int, int]:
+    """(samples kept, label frames kept): when the label count is more than one frame off ``n_samples // hop`` the
+    reference trims BOTH to the shorter one (sequential_dataset.py:169-180); otherwise nothing is trimmed."""
+    expected = n_samples // hop_length
+    if abs(n_label_frames - expected) > 1:
+        n = min(n_label_frames, expected)
+        return min(n_samples, n * hop_length), n
+    return n_samples, n_label_frames
+
+
+def recording_windows(audio: torch.Tensor, blendshapes: torch.Tensor, window_frames: int = 256, stride_frames: int = 1,
+                      hop_length: int = 533):
+    """All full windows of one recording, as zero-copy strided VIEWS on the tensors' own device (no gather kernel, no
+    host loop): ``audio`` (L,) and ``blendshapes`` (T, 52) -> ``{"audio": (N, window_frames * hop), "blendshapes":
+    (N, window_frames, 52), "start_frames": (N,)}``.  Window i covers label frames [i*stride, i*stride + W) and samples
+    [start*hop, end*hop); windows whose audio would run past the (aligned) recording are dropped, like the reference's
+    size check (sequential_dataset.py:182-196).  Feeding ``out["audio"]`` to ``SequentialDualStreamModel.forward`` gives
+    one frame per window -- the same frames the model produces when it slides over the whole recording itself."""
+    if audio.dim() != 1 or blendshapes.dim() != 2:
+        raise ValueError(f"audio must be (L,) and blendshapes (T, C), got {tuple(audio.shape)}, {tuple(blendshapes.shape)}")
+    if window_frames < 1 or stride_frames < 1 or hop_length < 1:
+        raise ValueError("window_frames, stride_frames and hop_length must be positive")
+    n_samples, n_frames = align_recording(audio.shape[0], blendshapes.shape[0], hop_length)
+    audio, blendshapes = audio[:n_samples], blendshapes[:n_frames]
+    w_samples = window_frames * hop_length
+    n = (n_frames - window_frames) // stride_frames + 1
+    # the reference yields a window only if its audio slice is complete
+    while n > 0 and (n - 1) * stride_frames * hop_length + w_samples > n_samples:
+        n -= 1
+    n = max(n, 0)
+    if n == 0:
+        return {"audio": audio.new_zeros((0, w_samples)), "blendshapes": blendshapes.new_zeros((0, window_frames, blendshapes.shape[1])),
+                "start_frames": torch.zeros(0, dtype=torch.long, device=audio.device)}
+    a = audio.as_strided((n, w_samples), (stride_frames * hop_length * audio.stride(0), audio.stride(0)))
+    b = blendshapes.as_strided((n, window_frames, blendshapes.shape[1]),
+                               (stride_frames * blendshapes.stride(0), blendshapes.stride(0), blendshapes.stride(1)))
+    return {"audio": a, "blendshapes": b,
+            "start_frames": torch.arange(n, device=audio.device, dtype=torch.long) * stride_frames}

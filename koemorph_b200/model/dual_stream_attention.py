@@ -75,15 +75,25 @@ class DualStreamCrossAttention(nn.Module):
                                                 nn.Linear(d_model // 2, 1), nn.Sigmoid())
         self.mel_norm = nn.LayerNorm(d_model)
         self.emotion_norm = nn.LayerNorm(d_model)
-        self.precision = "fp32"  # "fp32" (CUDA-core FMA) | "tf32" | "bf16" (tcgen05)
+        self.precision = "fp32"  # "fp32" (CUDA-core FMA) | "bf16" (bf16 operands on tcgen05, fp32 accumulation)
         self._folded: Dict = {}
+        # bumped by load_state_dict / invalidate_kernel_weights(): in-place edits through ``param.data`` do not change
+        # ``_version``, so code that writes weights that way must call invalidate_kernel_weights() itself
+        self._generation = 0
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_kernel_weights())
+
+    def invalidate_kernel_weights(self) -> None:
+        """Drop the folded kernel weights: call after editing parameters in place through ``.data`` (such writes do not
+        bump the version counter the cache key uses)."""
+        self._generation += 1
+        self._folded.clear()
 
     # ---- folded kernel weights, rebuilt when any parameter (or the compression layer) changes --------------
     def kernel_weights(self, compression: Optional[Dict[str, torch.Tensor]] = None) -> CoreWeights:
         named = list(self.named_parameters()) + list(self.named_buffers())
         comp = [] if compression is None else [compression["weight"], compression["bias"]]
         key = tuple((t.data_ptr(), t._version, str(t.device)) for _, t in named) + \
-            tuple((t.data_ptr(), t._version) for t in comp) + (self.temperature,)
+            tuple((t.data_ptr(), t._version) for t in comp) + (self.temperature, self._generation)
         slot = "comp" if compression is not None else "plain"
         hit = self._folded.get(slot)
         if hit is None or hit[0] != key:

@@ -39,14 +39,9 @@ class SequentialDualStreamModel(SimplifiedDualStreamModel):
         """reference :84,96."""
         return max(1, (audio_length // self.hop_length - self.window_frames) // self.stride_frames + 1)
 
-    @torch.no_grad()
-    def forward(self, audio: torch.Tensor, return_attention: bool = False,
-                egemaps: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        """reference :63-167."""
-        audio = self._check_audio(audio)
+    def _forward_frames(self, audio, eg, return_attention, out=None):
+        """The stateless part of forward(): (B, T_out, 52) smoothed blendshapes (+ sigmoid, attention)."""
         B, L = audio.shape
-        eg = self._check_egemaps(egemaps, B, audio.device)
-        fe = self._frontend(audio.device)
         hop, W, stride = self.hop_length, self.window_frames, self.stride_frames
         n_out = self.num_output_frames(L)
         T_w = W + 1                                        # librosa: 1 + (W * hop) // hop frames per window
@@ -55,24 +50,22 @@ class SequentialDualStreamModel(SimplifiedDualStreamModel):
         n_edge = 0 if (n_out == 1 and L <= self.window_samples) else math.ceil((self.n_fft // 2) / hop)
         if n_edge > _lib.MAX_EDGE:
             raise NotImplementedError(f"hop {hop} needs {n_edge} edge variants per side (max {_lib.MAX_EDGE})")
-        power, fmax = fe.power(audio, hop, n_frames)
-        powers, fmaxes = [power], [fmax]
-        for m in range(n_edge):
-            lo = fe.power(audio, hop, n_out, frame_offset=m, frame_step=stride, lo_rel=-m)
-            hi = fe.power(audio, hop, n_out, frame_offset=W - m, frame_step=stride, hi_rel=m)
-            powers += [lo[0], hi[0]]
-            fmaxes += [lo[1], hi[1]]
-        out, sig, attn = self._core_windows(powers, fmaxes, n_edge, B, n_frames, n_out, stride, T_w, eg,
-                                            return_attention)
-        if self.use_temporal_smoothing and n_out > 1:
-            alpha = float(torch.sigmoid(self.smoothing_alpha.detach().float()))
-            with torch.cuda.device(out.device):
-                _lib.check(_lib.load().koe_ema_scan(out.data_ptr(), B, n_out, alpha, None, 0,
-                                                    _lib.stream_ptr(out.device)), "koe_ema_scan")
-        # the reference leaves the smoothing state at the last frame of the sequence (:99,136)
-        self.prev_blendshapes = out[:, -1].clone() if self.use_temporal_smoothing else None
+        return self._forward_windows(audio, eg, n_frames, T_w, stride, n_out, n_edge, self.use_temporal_smoothing,
+                                     return_attention, out=out)
+
+    @torch.no_grad()
+    def forward(self, audio: torch.Tensor, return_attention: bool = False,
+                egemaps: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """reference :63-167.  ``out`` (extension): a preallocated contiguous (B, T_out, 52) float32 CUDA tensor that
+        receives the blendshapes (a corpus sweep lets every batch write where the results will be gathered)."""
+        audio = self._check_audio(audio)
+        B, L = audio.shape
+        eg = self._check_egemaps(egemaps, B, audio.device)
+        out, sig, attn = self._forward_frames(audio, eg, return_attention, out=out)
+        # the reference leaves the smoothing state at the last frame of the sequence (:99,136): a view, like its .detach()
+        self.prev_blendshapes = out[:, -1] if self.use_temporal_smoothing else None
         res = _package(out, sig, attn, return_attention)
-        res["num_frames"] = n_out
+        res["num_frames"] = out.shape[1]
         res["fps"] = self.target_fps
         res["emotion_backend"] = "egemaps_input"
         res["emotion_processing_time"] = 0.0

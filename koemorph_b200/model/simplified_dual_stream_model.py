@@ -60,6 +60,7 @@ class SimplifiedDualStreamModel(nn.Module):
             "weight": (torch.rand(256, 264, generator=gen) * 2 - 1) * bound,
             "bias": (torch.rand(256, generator=gen) * 2 - 1) * bound,
         }
+        self._compression_dev: Dict = {}
         self._mel_extractor = None
         if real_time_mode:
             from ..features.mel_sliding_window import MelSlidingWindowExtractor
@@ -92,6 +93,18 @@ class SimplifiedDualStreamModel(nn.Module):
         if tuple(weight.shape) != (256, 264) or tuple(bias.shape) != (256,):
             raise ValueError("compression layer must be weight (256, 264), bias (256,)")
         self._compression = {"weight": weight.detach().clone().float(), "bias": bias.detach().clone().float()}
+        self._compression_dev = {}
+        self.dual_stream_attention.invalidate_kernel_weights()   # a new tensor may reuse a freed address at version 0
+
+    def _alpha(self) -> float:
+        """sigmoid(smoothing_alpha) as a host float, read back once per parameter version (a device sync), not per call."""
+        p = self.smoothing_alpha
+        key = (p.data_ptr(), p._version, self.dual_stream_attention._generation)
+        hit = getattr(self, "_alpha_cache", None)
+        if hit is None or hit[0] != key:
+            hit = (key, float(torch.sigmoid(p.detach().float())))
+            self._alpha_cache = hit
+        return hit[1]
 
     def _frontend(self, device) -> LogMelFrontend:
         return LogMelFrontend.get(device, self.sample_rate, self.n_fft, self.n_mels, self.f_min, self.f_max)
@@ -135,10 +148,24 @@ class SimplifiedDualStreamModel(nn.Module):
         if egemaps is None:
             self._check_egemaps(None, 0, None)
         eg = _lib.require_cuda(egemaps, "egemaps")
-        eg = eg.reshape(eg.shape[0], 264)
-        w = self._compression["weight"].to(eg.device)
-        b = self._compression["bias"].to(eg.device)
-        return torch.addmm(b, eg, w.t()), {"backend_used": "egemaps_input", "processing_time": 0.0}
+        eg = eg.reshape(eg.shape[0], 264).contiguous()
+        out = torch.empty(eg.shape[0], 256, dtype=torch.float32, device=eg.device)
+        with torch.cuda.device(eg.device):
+            _lib.check(_lib.load().koe_affine_rows(eg.data_ptr(), eg.shape[0], 264, self._compression_t(eg.device).data_ptr(),
+                                                   self._compression_on(eg.device)["bias"].data_ptr(), 256, out.data_ptr(),
+                                                   _lib.stream_ptr(eg.device)), "koe_affine_rows")
+        return out, {"backend_used": "egemaps_input", "processing_time": 0.0}
+
+    def _compression_on(self, device) -> Dict[str, torch.Tensor]:
+        key = str(device)
+        if key not in self._compression_dev:
+            self._compression_dev = {key: {"weight": self._compression["weight"].to(device),
+                                           "bias": self._compression["bias"].to(device),
+                                           "weight_t": self._compression["weight"].t().contiguous().to(device)}}
+        return self._compression_dev[key]
+
+    def _compression_t(self, device) -> torch.Tensor:
+        return self._compression_on(device)["weight_t"]
 
     def align_features(self, mel_features, emotion_features):
         """No-op for concatenated eGeMAPS (reference :317-322)."""
@@ -154,10 +181,14 @@ class SimplifiedDualStreamModel(nn.Module):
             self.prev_blendshapes = blendshapes.detach().clone()
             return blendshapes
         x = _lib.require_cuda(blendshapes, "blendshapes").clone()
-        alpha = float(torch.sigmoid(self.smoothing_alpha.detach().float()))
+        # the state may be a view of an earlier result (SequentialDualStreamModel.forward leaves out[:, -1] here): the scan
+        # updates its state in place, so it gets a private contiguous copy
+        state = self.prev_blendshapes.clone(memory_format=torch.contiguous_format)
+        alpha = self._alpha()
         with torch.cuda.device(x.device):
-            _lib.check(_lib.load().koe_ema_scan(x.data_ptr(), B, 1, alpha, self.prev_blendshapes.data_ptr(), 1,
+            _lib.check(_lib.load().koe_ema_scan(x.data_ptr(), B, 1, alpha, state.data_ptr(), 1,
                                                 _lib.stream_ptr(x.device)), "koe_ema_scan")
+        self.prev_blendshapes = state
         return x
 
     def _core_windows(self, power_list, fmax_list, n_edge, B, n_frames, n_out, stride, frames_per_window, eg,
@@ -188,6 +219,66 @@ class SimplifiedDualStreamModel(nn.Module):
                 "koe_dual_stream_windows")
         return out, sig, attn
 
+    def _forward_windows(self, audio, eg, n_frames, frames_per_window, stride, n_out, n_edge, smooth, return_attention,
+                         out=None):
+        """koe_forward_windows: frontend (+ edge variants), emotion stream, core and EMA scan as ONE native call.
+        Returns (out (B, n_out, 52), sigmoid or None, attention or None); ``out`` may be preallocated."""
+        lib = _lib.load()
+        dev = audio.device
+        B, L = audio.shape
+        w = self.dual_stream_attention.kernel_weights(self._compression)
+        fe = self._frontend(dev)
+        if out is None:
+            out = torch.empty(B, n_out, 52, dtype=torch.float32, device=dev)
+        elif out.shape != (B, n_out, 52) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+            raise ValueError(f"out must be a contiguous float32 ({B}, {n_out}, 52) tensor on {dev}")
+        # one workspace allocation per call: mel power (dB) of the global frames and of the edge variants, their per-frame
+        # maxima, the emotion stream's per-clip value
+        n_main, n_var = B * n_frames, B * n_out
+        floats = n_main * 81 + 2 * n_edge * n_var * 81 + B
+        ws = torch.empty(floats + 4, dtype=torch.float32, device=dev)
+        a = _lib.ForwardArgs()
+        a.frontend, a.weights = fe._h, C.addressof(w.struct)
+        a.audio, a.audio_stride = audio.data_ptr(), audio.stride(0)
+        a.n_clips, a.n_samples, a.hop = B, L, self.hop_length
+        a.n_frames, a.frames_per_window, a.stride_frames, a.n_out, a.n_edge = n_frames, frames_per_window, stride, n_out, n_edge
+        a.egemaps = eg.data_ptr()
+        base, off = ws.data_ptr(), 0
+        a.power[0] = base
+        off += n_main * 80
+        for j in range(1, 1 + 2 * n_edge):
+            a.power[j] = base + 4 * off
+            off += n_var * 80
+        a.frame_max[0] = base + 4 * off
+        off += n_main
+        for j in range(1, 1 + 2 * n_edge):
+            a.frame_max[j] = base + 4 * off
+            off += n_var
+        a.expr_sigmoid = base + 4 * off
+        sig = torch.empty(B, n_out, 52, dtype=torch.float32, device=dev) if return_attention else None
+        attn = torch.empty(B, n_out, 28, 80, dtype=torch.float32, device=dev) if return_attention else None
+        a.out = out.data_ptr()
+        a.sigmoid_out = sig.data_ptr() if sig is not None else None
+        a.attn_out = attn.data_ptr() if attn is not None else None
+        a.alpha = self._alpha() if smooth else 0.0
+        a.smooth = 1 if smooth else 0
+        a.precision = _lib.PRECISIONS[self.precision]
+        with torch.cuda.device(dev):
+            _lib.check(lib.koe_forward_windows(C.byref(a), _lib.stream_ptr(dev)), "koe_forward_windows")
+        return out, sig, attn
+
+    def _single_frames(self, audio, eg, return_attention, out=None):
+        """The stateless part of forward(): (B, 52) pre-smoothing blendshapes (+ sigmoid, attention)."""
+        B, L = audio.shape
+        T = 1 + L // self.hop_length
+        o, sig, attn = self._forward_windows(audio, eg, T, T, 1, 1, 0, False, return_attention,
+                                             out=None if out is None else out.view(B, 1, 52))
+        return o[:, 0], None if sig is None else sig[:, 0], None if attn is None else attn[:, 0]
+
+    def _forward_frames(self, audio, eg, return_attention, out=None):
+        """What HostPipeline runs per chunk: the stateless part of THIS class's forward (overridden by the sequence model)."""
+        return self._single_frames(audio, eg, return_attention, out=out)
+
     @torch.no_grad()
     def forward(self, audio: torch.Tensor, return_attention: bool = False,
                 egemaps: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
@@ -195,12 +286,8 @@ class SimplifiedDualStreamModel(nn.Module):
         audio = self._check_audio(audio)
         B, L = audio.shape
         eg = self._check_egemaps(egemaps, B, audio.device)
-        fe = self._frontend(audio.device)
-        T = 1 + L // self.hop_length
-        power, fmax = fe.power(audio, self.hop_length, T)
-        out, sig, attn = self._core_windows([power], [fmax], 0, B, T, 1, 1, T, eg, return_attention)
-        res = _package(out[:, 0], None if sig is None else sig[:, 0], None if attn is None else attn[:, 0],
-                       return_attention)
+        out, sig, attn = self._single_frames(audio, eg, return_attention)
+        res = _package(out, sig, attn, return_attention)
         res["blendshapes"] = self.apply_temporal_smoothing(res["blendshapes"])
         return res
 

@@ -31,11 +31,23 @@ import torch
 
 from . import koemorph_oracle as O
 
+# /root/reference in the build container; on the GPU box the byte-identical copies staged by oracle/stage_reference.py
+# (oracle/_ref, git-ignored, shipped with the gpurun snapshot)
+_STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REFERENCE_ROOT = os.environ.get("KOEMORPH_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "model")) and os.path.isdir(os.path.join(_STAGED_ROOT, "src", "model")):
+    REFERENCE_ROOT = _STAGED_ROOT
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "model"))
+
+
+def reference_kind() -> str:
+    """"tree" (the reference checkout itself), "staged" (oracle/_ref copies) or "absent"."""
+    if not reference_available():
+        return "absent"
+    return "staged" if REFERENCE_ROOT == _STAGED_ROOT else "tree"
 
 
 def _install_stubs():

@@ -73,3 +73,9 @@ for name, order in variants:
     print(f"{name:36s} median {med:7.1f} us  min {mn:7.1f} us  bit-identical {same}", flush=True)
     assert same, name
 set_variant(0x44)
+
+# timing probe (results are not written): FFT + loads only, no CTA barrier / mel phase / store phase
+set_variant(0x100)
+med, mn = timed(out)
+print(f"{'probe: FFT + loads only, free running':36s} median {med:7.1f} us  min {mn:7.1f} us")
+set_variant(0x44)

@@ -373,3 +373,127 @@ def test_logmel_launch_order_over_ragged_shapes(K, L, hop, n_frames, frame_offse
         if big.any():
             assert np.abs(db[b, :have] - 10 * np.log10(np.maximum(ref, 1e-10)))[big].max() < 8.7e-4
         np.testing.assert_allclose(fmax[b].cpu().numpy(), db[b].max(axis=1), rtol=1e-6)
+
+
+# ---- round 2: host pipeline state handling, fused native forward, public emotion entry, weight-cache invalidation --------
+def test_host_pipeline_with_the_single_frame_model_matches_one_forward(K):
+    """HostPipeline(SimplifiedDualStreamModel): chunking must not change the result.  forward() blends every call with the
+    previous call's output (reference :341-368); a chunked run has to apply that once over the whole batch."""
+    from koemorph_b200.infer import HostPipeline
+    spec = dict(fps=30, wseed=1235, style="stress", iseed=77, kind="speechlike", B=11, L=60000)
+    m, _ = _model(K, spec, False)
+    audio, eg = _inputs(spec)
+    audio2 = torch.roll(audio, 1, 0).contiguous()
+    want1 = m(audio, egemaps=eg)["blendshapes"].clone()
+    want2 = m(audio2, egemaps=eg)["blendshapes"].clone()         # second call: EMA against the first
+    m.reset_temporal_state()
+    pipe = HostPipeline(m, chunk_clips=4)                         # 3 chunks: 4 + 4 + 3 clips on two streams
+    got1 = pipe(audio.cpu().pin_memory(), eg.cpu().pin_memory()).clone()
+    got2 = pipe(audio2.cpu().pin_memory(), eg.cpu().pin_memory()).clone()
+    assert got1.shape == (11, 52)
+    assert torch.equal(got1, want1.cpu()) and torch.equal(got2, want2.cpu())
+    assert not torch.equal(got1, got2)
+
+
+def test_host_pipeline_leaves_the_sequence_models_state(K):
+    from koemorph_b200.infer import HostPipeline
+    spec = dict(fps=30, wseed=1235, style="stress", iseed=78, kind="noise", B=5, L=136000 + 3 * 533)
+    m, _ = _model(K, spec, True)
+    audio, eg = _inputs(spec)
+    want = m(audio, egemaps=eg)["blendshapes"].clone()
+    state = m.prev_blendshapes.clone()
+    m.reset_temporal_state()
+    got = HostPipeline(m, chunk_clips=2)(audio.cpu().pin_memory(), eg.cpu().pin_memory())
+    assert torch.equal(got, want.cpu())
+    assert torch.equal(m.prev_blendshapes, state)
+    # the state a later single-frame call smooths against is the last frame, whatever its memory layout
+    nxt = m.forward_single_frame(audio[:, :136000].contiguous(), egemaps=eg)["blendshapes"]
+    alpha = torch.sigmoid(m.smoothing_alpha).item()
+    raw = m._single_frames(audio[:, :136000].contiguous(), eg, False)[0]
+    _close(nxt, alpha * raw + (1 - alpha) * want[:, -1], 0, 1e-7, "single frame after a sequence")
+    assert torch.equal(want, m(audio, egemaps=eg)["blendshapes"]), "the earlier result tensor was modified"
+
+
+def test_forward_out_argument_and_fused_call_equal_the_separate_entry_points(K):
+    """koe_forward_windows (one native call, programmatic dependent launch inside) against the same kernels issued one by
+    one through the public single-kernel entries."""
+    spec = dict(fps=30, wseed=1235, style="stress", iseed=79, kind="speechlike", B=3, L=136000 + 7 * 533)
+    m, _ = _model(K, spec, True)
+    audio, eg = _inputs(spec)
+    for precision in ("fp32", "bf16"):
+        m.precision = precision
+        res = m(audio, egemaps=eg, return_attention=True)
+        n_out, W = m.num_output_frames(audio.shape[1]), 256
+        assert n_out == 7
+        buf = torch.full((3, n_out, 52), float("nan"), device="cuda")
+        res2 = m(audio, egemaps=eg, out=buf)
+        assert res2["blendshapes"].data_ptr() == buf.data_ptr() and torch.equal(buf, res["blendshapes"])
+        # the decomposed path: frontend launches, emotion stream, core, EMA through the public entries
+        fe = m._frontend(audio.device)
+        n_frames = n_out - 1 + W + 1
+        power, fmax = fe.power(audio, 533, n_frames)
+        lo = fe.power(audio, 533, n_out, frame_offset=0, frame_step=1, lo_rel=0)
+        hi = fe.power(audio, 533, n_out, frame_offset=W, frame_step=1, hi_rel=0)
+        out, sig, attn = m._core_windows([power, lo[0], hi[0]], [fmax, lo[1], hi[1]], 1, 3, n_frames, n_out, 1, W + 1, eg, True)
+        assert torch.equal(sig, res["mel_blendshapes"] + res["emotion_blendshapes"])
+        _close(attn, res["mel_attention_weights"], 0, 1e-6, "attention weights")  # head average accumulated with atomics
+        from koemorph_b200 import _lib
+        alpha = float(torch.sigmoid(m.smoothing_alpha.detach()))
+        _lib.check(_lib.load().koe_ema_scan(out.data_ptr(), 3, n_out, alpha, None, 0, _lib.stream_ptr(out.device)))
+        assert torch.equal(out, res["blendshapes"])
+    with pytest.raises(ValueError):
+        m(audio, egemaps=eg, out=torch.empty(3, 8, 52, device="cuda"))
+
+
+def test_public_emotion_entry_sees_the_previous_kernels_writes(K):
+    """koe_emotion_stream from the public ABI keeps full stream order: its input may be produced by the kernel queued just
+    before it (it used to start early under programmatic dependent launch)."""
+    import ctypes as C
+    from koemorph_b200 import _lib
+    spec = dict(fps=30, wseed=1235, style="stress", iseed=80, kind="noise", B=4096, L=1)
+    m, _ = _model(K, spec, False)
+    w = m.dual_stream_attention.kernel_weights(m._compression)
+    lib = _lib.load()
+    eg = torch.randn(4096, 264, device="cuda")
+    want = torch.empty(4096, device="cuda")
+    _lib.check(lib.koe_emotion_stream(C.byref(w.struct), eg.data_ptr(), 4096, want.data_ptr(), _lib.stream_ptr(eg.device)))
+    torch.cuda.synchronize()
+    big = torch.randn(64, 1 << 20, device="cuda")
+    for _ in range(5):
+        src = torch.zeros_like(eg)
+        got = torch.empty(4096, device="cuda")
+        big.mul_(1.0001)                       # keep the device busy so that the next kernels queue up
+        src.copy_(eg)                          # producer of the input: the kernel right before the emotion stream
+        _lib.check(lib.koe_emotion_stream(C.byref(w.struct), src.data_ptr(), 4096, got.data_ptr(), _lib.stream_ptr(eg.device)))
+        assert torch.equal(got, want)
+
+
+def test_extract_emotion_features_is_the_compression_layer(K):
+    spec = dict(fps=30, wseed=1235, style="stress", iseed=81, kind="noise", B=7, L=1)
+    m, w = _model(K, spec, False)
+    eg = torch.randn(7, 264, device="cuda")
+    got, meta = m.extract_emotion_features(egemaps=eg)
+    ref = eg.double().cpu() @ torch.from_numpy(w["compression.weight"]).double().t() + torch.from_numpy(w["compression.bias"]).double()
+    _close(got, ref, 1e-5, 1e-6, "264 -> 256 compression")
+    assert meta["backend_used"] == "egemaps_input"
+    got3, _ = m.extract_emotion_features(egemaps=eg.view(7, 3, 88))
+    assert torch.equal(got3, got)
+
+
+def test_folded_weights_follow_in_place_edits_after_invalidate(K):
+    spec = dict(fps=30, wseed=1234, style="init", iseed=82, kind="noise", B=2, L=136000)
+    m, _ = _model(K, spec, False)
+    audio, eg = _inputs(spec)
+    a = m(audio, egemaps=eg)["blendshapes"].clone()
+    m.reset_temporal_state()
+    m.dual_stream_attention.mel_weights.data.mul_(2.0)            # .data edit: no version bump
+    m.dual_stream_attention.invalidate_kernel_weights()
+    b = m(audio, egemaps=eg)["blendshapes"].clone()
+    assert not torch.equal(a, b)
+    m.reset_temporal_state()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd["dual_stream_attention.mel_weights"] /= 2.0
+    m.load_state_dict(sd)                                          # post hook invalidates
+    assert torch.equal(m(audio, egemaps=eg)["blendshapes"], a)
+    with pytest.raises(ValueError):
+        m.precision = "tf32"

@@ -81,3 +81,72 @@ def test_stft_golden_fixture_is_complete():
         assert np.isfinite(data[f"{name}/log_mel"]).all()
     x = stft_inputs(11, 2, 16000, "noise")
     assert x.shape == (2, 16000) and torch.equal(x, stft_inputs(11, 2, 16000, "noise"))
+
+
+# ---- window slicing of long recordings against the UNMODIFIED reference dataset class (tests/golden/make_golden_dataset.py)
+def _dataset_cases():
+    import os
+    import numpy as np
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset_windows.npz")
+    data = np.load(here)
+    return json.loads(str(data["cases"])), data
+
+
+def _check_recording_windows(device):
+    import numpy as np
+    cases, data = _dataset_cases()
+    assert len(cases) >= 7
+    for name, n_samples, n_labels, W, stride, fps in cases:
+        rng = np.random.default_rng(int(data[f"{name}.seed"]))
+        audio = torch.from_numpy(rng.standard_normal(n_samples).astype(np.float32)).to(device)
+        labels = torch.from_numpy(rng.random((n_labels, 52)).astype(np.float32)).to(device)
+        hop = int(16000 / fps)
+        out = kio.recording_windows(audio, labels, W, stride, hop)
+        want_start = data[f"{name}.start_frames"]
+        assert out["start_frames"].cpu().tolist() == want_start.tolist(), name
+        assert out["audio"].shape == (len(want_start), W * hop) and out["blendshapes"].shape == (len(want_start), W, 52)
+        assert out["audio"].device == audio.device
+        if len(want_start) == 0:
+            continue
+        assert out["audio"].data_ptr() == audio.data_ptr(), "windows must be views, not copies"
+        np.testing.assert_allclose(out["audio"].double().sum(1).cpu().numpy(), data[f"{name}.audio_sum"], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(out["blendshapes"].double().sum((1, 2)).cpu().numpy(), data[f"{name}.label_sum"], rtol=0, atol=1e-9)
+        fl = torch.stack([out["audio"][:, 0], out["audio"][:, -1]], 1).cpu().numpy()
+        assert (fl == data[f"{name}.audio_first_last"]).all(), name
+        # the window grid of the model-side helper describes the same windows
+        n_s, n_f = kio.align_recording(n_samples, n_labels, hop)
+        grid = [g for g in kio.window_grid(n_f, W, stride, hop) if g[3] <= n_s]
+        assert [g[0] for g in grid] == want_start.tolist()
+
+
+def test_recording_windows_match_the_reference_dataset_cpu():
+    _check_recording_windows("cpu")
+
+
+@pytest.mark.gpu
+def test_recording_windows_match_the_reference_dataset_on_device():
+    _check_recording_windows("cuda")
+
+
+@pytest.mark.gpu
+def test_windows_of_a_recording_fed_as_clips_equal_the_sliding_forward():
+    """Window i of a long recording, cut out on the device and fed to the model as a clip of its own, gives frame i of the
+    model's own slide over the whole recording (smoothing off: it couples consecutive frames)."""
+    import numpy as np
+    import koemorph_b200 as K
+    from oracle import koemorph_oracle as O
+    w = O.make_weights(1235, 30, style="stress")
+    m = K.SequentialDualStreamModel(stride_frames=2).cuda().eval()
+    m.load_state_dict(O.model_state_dict(w), strict=True)
+    m.set_compression_layer(torch.from_numpy(w["compression.weight"]), torch.from_numpy(w["compression.bias"]))
+    m.use_temporal_smoothing = False
+    audio, eg = O.make_inputs(4321, 1, 136000 + 11 * 533, "speechlike")
+    audio, eg = torch.from_numpy(audio).cuda(), torch.from_numpy(eg).cuda()
+    whole = m(audio, egemaps=eg)["blendshapes"][0]                       # (T_out, 52)
+    labels = torch.zeros(audio.shape[1] // 533, 52, device="cuda")
+    wins = kio.recording_windows(audio[0], labels, 256, 2, 533)
+    assert wins["audio"].shape[0] == whole.shape[0] == 6
+    per_window = m(wins["audio"].contiguous(), egemaps=eg.expand(6, -1).contiguous())["blendshapes"][:, 0]
+    # not bitwise: a frame's rounding depends on the frame it shares its complex transform with, and the window-edge frames
+    # are paired differently in the two runs
+    assert (per_window - whole).abs().max().item() < 2e-7
