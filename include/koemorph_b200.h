@@ -78,6 +78,8 @@ typedef struct {
   int32_t window_normalized;
   int32_t log_mode;
   float log_eps;
+  int32_t win_length; /* 0 = n_fft; else the periodic Hann of win_length <= n_fft points, centred in the n_fft frame
+                         (librosa / torch.stft semantics of win_length < n_fft) */
 } koe_frontend_config;
 int koe_frontend_create_ex(const koe_frontend_config* cfg, koe_frontend_t** out);
 int koe_frontend_destroy(koe_frontend_t* fe);
@@ -256,12 +258,23 @@ int koe_dual_stream_ring(const koe_core_weights* w, const float* power_ring, con
                          void* stream);
 
 /*
+ * General form for hop < n_fft/2 (60 fps: hop 266, two edge frames per window side): power[0] / frame_max[0] the plain
+ * ring, power[1 + 2m] the ring of lo-edge variant m (frame g with everything before (g - m) * hop zeroed, in the slot of
+ * global frame g), power[2 + 2m] the per-stream row of hi-edge variant m (frame T-1-m of the window that ends now).
+ */
+int koe_dual_stream_ring_edges(const koe_core_weights* w, const float* const* power, const float* const* frame_max,
+                               int n_edge, int n_streams, int ring_frames, int ring_base, int frames_per_window,
+                               const float* expr_sigmoid, float* out, float* sigmoid_out, float* attn_out, int precision,
+                               void* stream);
+
+/*
  * One hop of every stream as ONE call (the real-time loop of scripts/rt.py:465-519 over
  * SimplifiedDualStreamModel.process_audio_frame_realtime, src/model/simplified_dual_stream_model.py:452-500, with the
  * sliding window of SequentialDualStreamModel.forward at stride 1): appends hop_audio to each stream's audio tail,
- * computes the three new frames of the step (plain, window-start and window-end variants, SURVEY.md section 8 note E)
- * into the streams' rings, and -- once window_frames hops have been pushed -- runs koe_dual_stream_ring on the window
- * that ends at the newest sample and smooths the result (koe_ema_scan with n_out = 1).  Queues five kernels; replaces the
+ * computes the new frames of the step (plain, window-start and window-end variants, SURVEY.md section 8 note E: three
+ * at 30 fps, five at 60 fps where hop < n_fft/2) into the streams' rings, and -- once window_frames hops have been pushed --
+ * runs koe_dual_stream_ring on the window that ends at the newest sample and smooths the result (koe_ema_scan with
+ * n_out = 1).  Queues five kernels (seven at 60 fps); replaces the
  * Python driver's six separate calls (about 150 us of host time per hop).  All buffers are caller-owned device memory
  * and persist between calls; `step` counts the hops pushed before this one (0, 1, 2, ...) and selects the ping-pong tail
  * buffer (reads tail[step & 1], writes tail[(step + 1) & 1]) and the ring slot.  *emitted = 1 when `out` holds a frame.
@@ -271,10 +284,15 @@ typedef struct {
   const koe_core_weights* weights;
   int32_t n_streams, hop, window_frames, half_fft; /* half_fft = n_fft / 2 (512) */
   const float* hop_audio;                          /* [n_streams][hop]: the next hop of every stream */
-  float* tail[2];                                  /* [n_streams][half_fft + hop] each; zero before the first hop */
+  float* tail[2];                                  /* [n_streams][half_fft + n_edge * hop] each, n_edge = ceil(half_fft / hop);
+                                                      zero before the first hop */
   float* ring_f; float* fmax_f;                    /* [n_streams][window_frames][80], [n_streams][window_frames] */
   float* ring_r; float* fmax_r;                    /* same shapes: the window-start variants */
   float* row_l; float* fmax_l;                     /* [n_streams][80], [n_streams]: the window-end variant */
+  /* hop < n_fft/2 (60 fps): the second edge frame of either side -- frame g with everything before (g - 1) * hop zeroed
+   * (ring) and the last-but-one frame of the window that ends now (row); NULL when hop >= n_fft/2 */
+  float* ring_r2; float* fmax_r2;
+  float* row_l2; float* fmax_l2;
   const float* expr_sigmoid;                       /* [n_streams], from koe_emotion_stream */
   float* out;                                      /* [n_streams][52] */
   float* ema_state;                                /* [n_streams][52], or NULL: no temporal smoothing */

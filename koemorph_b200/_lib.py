@@ -56,7 +56,9 @@ class StreamArgs(C.Structure):
                 ("n_streams", C.c_int32), ("hop", C.c_int32), ("window_frames", C.c_int32), ("half_fft", C.c_int32),
                 ("hop_audio", C.c_void_p), ("tail", C.c_void_p * 2),
                 ("ring_f", C.c_void_p), ("fmax_f", C.c_void_p), ("ring_r", C.c_void_p), ("fmax_r", C.c_void_p),
-                ("row_l", C.c_void_p), ("fmax_l", C.c_void_p), ("expr_sigmoid", C.c_void_p), ("out", C.c_void_p),
+                ("row_l", C.c_void_p), ("fmax_l", C.c_void_p),
+                ("ring_r2", C.c_void_p), ("fmax_r2", C.c_void_p), ("row_l2", C.c_void_p), ("fmax_l2", C.c_void_p),
+                ("expr_sigmoid", C.c_void_p), ("out", C.c_void_p),
                 ("ema_state", C.c_void_p), ("alpha", C.c_float), ("has_state", C.c_int32), ("precision", C.c_int32),
                 ("step", C.c_int64)]
 
@@ -77,7 +79,8 @@ class FrontendConfig(C.Structure):
     """koe_frontend_config (include/koemorph_b200.h)."""
     _fields_ = [("device", C.c_int32), ("sample_rate", C.c_int32), ("n_fft", C.c_int32), ("n_mels", C.c_int32),
                 ("fmin", C.c_float), ("fmax", C.c_float), ("mel_scale", C.c_int32), ("mel_norm", C.c_int32),
-                ("window_normalized", C.c_int32), ("log_mode", C.c_int32), ("log_eps", C.c_float)]
+                ("window_normalized", C.c_int32), ("log_mode", C.c_int32), ("log_eps", C.c_float),
+                ("win_length", C.c_int32)]
 
 
 _lib = None
@@ -100,6 +103,9 @@ _SIGNATURES = {
     "koe_dual_stream_ring": (C.c_int, [C.POINTER(CoreWeightsStruct), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "koe_dual_stream_ring_edges": (C.c_int, [C.POINTER(CoreWeightsStruct), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "koe_logmel_normalise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "koe_pcm16_to_float": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -29,8 +29,9 @@ __device__ __forceinline__ int window_variant(const CoreParams& p, int k) {
   return 0;
 }
 __device__ __forceinline__ long long window_row(const CoreParams& p, int variant, int b, int wi, int k) {
-  if (p.ring_frames > 0)
-    return variant == 2 ? (long long)b : (long long)b * p.ring_frames + (p.ring_base + k) % p.ring_frames;
+  if (p.ring_frames > 0)  // plain and lo-edge rows are ring slots of the global frame; a hi-edge row (variants 2, 4) is per stream
+    return variant > 0 && (variant & 1) == 0 ? (long long)b
+                                             : (long long)b * p.ring_frames + (p.ring_base + k) % p.ring_frames;
   return variant == 0 ? (long long)b * p.n_frames + (long long)wi * p.stride_frames + k
                       : (long long)b * p.n_out + wi;
 }

@@ -751,26 +751,25 @@ extern "C" int koe_dual_stream_windows(const koe_core_weights* w, const float* c
   return launch_core(p, precision, (cudaStream_t)stream);
 }
 
-extern "C" int koe_dual_stream_ring(const koe_core_weights* w, const float* power_ring, const float* fmax_ring,
-                                    const float* power_lo_ring, const float* fmax_lo_ring, const float* power_hi,
-                                    const float* fmax_hi, int n_streams, int ring_frames, int ring_base,
-                                    int frames_per_window, const float* expr_sigmoid, float* out, float* sigmoid_out,
-                                    float* attn_out, int precision, void* stream) {
+extern "C" int koe_dual_stream_ring_edges(const koe_core_weights* w, const float* const* power,
+                                          const float* const* frame_max, int n_edge, int n_streams, int ring_frames,
+                                          int ring_base, int frames_per_window, const float* expr_sigmoid, float* out,
+                                          float* sigmoid_out, float* attn_out, int precision, void* stream) {
   if (int rc = validate_weights(w)) return rc;
-  KOE_REQUIRE(power_ring && fmax_ring && power_lo_ring && fmax_lo_ring && power_hi && fmax_hi && expr_sigmoid && out,
+  KOE_REQUIRE(power != nullptr && frame_max != nullptr && expr_sigmoid != nullptr && out != nullptr,
               "koe_dual_stream_ring: NULL argument");
-  KOE_REQUIRE(n_streams >= 0 && ring_base >= 0 && frames_per_window >= 3 && ring_frames >= frames_per_window - 1,
+  KOE_REQUIRE(n_edge >= 1 && n_edge <= KOE_MAX_EDGE, "koe_dual_stream_ring: n_edge out of range");
+  KOE_REQUIRE(n_streams >= 0 && ring_base >= 0 && frames_per_window > 2 * n_edge && ring_frames >= frames_per_window - 1,
               "koe_dual_stream_ring: bad sizes (the ring must hold every plain frame of a window)");
-  KOE_REQUIRE(((reinterpret_cast<uintptr_t>(power_ring) | reinterpret_cast<uintptr_t>(power_lo_ring) |
-                reinterpret_cast<uintptr_t>(power_hi)) & 15) == 0,
-              "koe_dual_stream_ring: mel rows must be 16-byte aligned");
   if (n_streams == 0) return KOE_OK;
   CoreParams p{};
   p.w = *w;
-  p.power[0] = power_ring, p.fmax[0] = fmax_ring;
-  p.power[1] = power_lo_ring, p.fmax[1] = fmax_lo_ring;
-  p.power[2] = power_hi, p.fmax[2] = fmax_hi;
-  p.n_edge = 1;
+  for (int j = 0; j < 1 + 2 * n_edge; ++j) {
+    KOE_REQUIRE(power[j] != nullptr && frame_max[j] != nullptr, "koe_dual_stream_ring: NULL buffer %d", j);
+    KOE_REQUIRE((reinterpret_cast<uintptr_t>(power[j]) & 15) == 0, "koe_dual_stream_ring: mel rows must be 16-byte aligned");
+    p.power[j] = power[j], p.fmax[j] = frame_max[j];
+  }
+  p.n_edge = n_edge;
   p.n_clips = n_streams;
   p.n_frames = ring_frames;
   p.n_out = 1;
@@ -784,6 +783,17 @@ extern "C" int koe_dual_stream_ring(const koe_core_weights* w, const float* powe
   p.ring_frames = ring_frames;
   p.ring_base = ring_base % ring_frames;
   return launch_core(p, precision, (cudaStream_t)stream);
+}
+
+extern "C" int koe_dual_stream_ring(const koe_core_weights* w, const float* power_ring, const float* fmax_ring,
+                                    const float* power_lo_ring, const float* fmax_lo_ring, const float* power_hi,
+                                    const float* fmax_hi, int n_streams, int ring_frames, int ring_base,
+                                    int frames_per_window, const float* expr_sigmoid, float* out, float* sigmoid_out,
+                                    float* attn_out, int precision, void* stream) {
+  const float* power[3] = {power_ring, power_lo_ring, power_hi};
+  const float* fmax[3] = {fmax_ring, fmax_lo_ring, fmax_hi};
+  return koe_dual_stream_ring_edges(w, power, fmax, 1, n_streams, ring_frames, ring_base, frames_per_window, expr_sigmoid,
+                                    out, sigmoid_out, attn_out, precision, stream);
 }
 
 extern "C" int koe_dual_stream_features(const koe_core_weights* w, const float* mel_long, int n_long,

@@ -740,6 +740,7 @@ extern "C" int koe_frontend_create(int device, int sample_rate, int n_fft, int n
   c.window_normalized = 0;
   c.log_mode = KOE_LOG_DB;
   c.log_eps = 0.0f;
+  c.win_length = 0;
   return koe_frontend_create_ex(&c, out);
 }
 
@@ -790,11 +791,17 @@ extern "C" int koe_frontend_create_ex(const koe_frontend_config* cfg, koe_fronte
   }
   // periodic Hann of n_fft points, centred in the 1024-sample frame; torchaudio's normalized=True ("window") divides the
   // STFT by sqrt(sum w^2), i.e. the power by sum w^2: folded into the sparse weights below
+  const int win_length = cfg->win_length > 0 ? cfg->win_length : n_fft;
+  if (win_length > n_fft || win_length < 2) {
+    delete fe;
+    cudaSetDevice(prev);
+    return fail(KOE_E_INVALID, "koe_frontend_create: win_length %d must be in [2, n_fft = %d]", win_length, n_fft);
+  }
   std::vector<float> hann(kFrameLen, 0.0f);
   double wsum2 = 0.0;
-  for (int n = 0; n < n_fft; ++n) {
-    const double w = 0.5 - 0.5 * std::cos(2.0 * M_PI * n / n_fft);
-    hann[(kFrameLen - n_fft) / 2 + n] = (float)w;
+  for (int n = 0; n < win_length; ++n) {  // window of win_length points centred in the n_fft frame (pad_center)
+    const double w = 0.5 - 0.5 * std::cos(2.0 * M_PI * n / win_length);
+    hann[(kFrameLen - n_fft) / 2 + (n_fft - win_length) / 2 + n] = (float)w;
     wsum2 += (double)(float)w * (double)(float)w;
   }
   const float wscale = cfg->window_normalized ? (float)(0.25 / wsum2) : 0.25f;  // 0.25: the kernel leaves 4 |X|^2
@@ -866,7 +873,7 @@ extern "C" int koe_frontend_create_ex(const koe_frontend_config* cfg, koe_fronte
   }
   // the unrolled filterbank phase applies when the bank has the structure of melbank_default.inc and its weights
   // (computed above from the run-time arguments) equal the baked-in ones to within one float32 ulp
-  fe->default_bank = sub == 1 && !cfg->window_normalized && fe->n_bins == kDefNumBins && tables[0] == kDefFirstBin &&
+  fe->default_bank = sub == 1 && win_length == n_fft && !cfg->window_normalized && fe->n_bins == kDefNumBins && tables[0] == kDefFirstBin &&
                      std::equal(bin_group.begin(), bin_group.end(), kDefBinGroup);
   for (int i = 0; fe->default_bank && i < kDefNumBins; ++i) {
     const float got[2] = {binw[i].x, binw[i].y}, want[2] = {kDefBinW[2 * i], kDefBinW[2 * i + 1]};

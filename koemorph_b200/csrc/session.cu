@@ -36,14 +36,19 @@ extern "C" int koe_stream_push(const koe_stream_args* a, int* emitted, void* str
   KOE_REQUIRE(a->frontend != nullptr && a->weights != nullptr, "koe_stream_push: NULL frontend / weights");
   KOE_REQUIRE(a->n_streams >= 0 && a->hop > 0 && a->window_frames > 0 && a->half_fft > 0 && a->step >= 0,
               "koe_stream_push: bad geometry");
-  KOE_REQUIRE(a->hop >= a->half_fft, "koe_stream_push: implements the hop >= n_fft/2 geometry (one edge frame per window side)");
+  // frames within n_fft/2 of a window edge see zeros beyond it: ceil(half / hop) frames per side (1 at 30 fps, 2 at 60 fps)
+  const int n_edge = (a->half_fft + a->hop - 1) / a->hop;
+  KOE_REQUIRE(n_edge >= 1 && n_edge <= KOE_MAX_EDGE, "koe_stream_push: hop %d needs %d edge frames per window side (max %d)",
+              a->hop, n_edge, KOE_MAX_EDGE);
   KOE_REQUIRE(a->hop_audio && a->tail[0] && a->tail[1] && a->ring_f && a->fmax_f && a->ring_r && a->fmax_r && a->row_l &&
                   a->fmax_l && a->expr_sigmoid && a->out,
               "koe_stream_push: NULL buffer");
+  KOE_REQUIRE(n_edge == 1 || (a->ring_r2 && a->fmax_r2 && a->row_l2 && a->fmax_l2),
+              "koe_stream_push: hop < n_fft/2 needs the second edge buffers (ring_r2, row_l2)");
   *emitted = 0;
   if (a->n_streams == 0) return KOE_OK;
   cudaStream_t stream = (cudaStream_t)stream_v;
-  const int S = a->n_streams, hop = a->hop, W = a->window_frames, half = a->half_fft, tail_len = half + hop;
+  const int S = a->n_streams, hop = a->hop, W = a->window_frames, half = a->half_fft, tail_len = half + n_edge * hop;
   const int64_t n = a->step;
   const float* old_tail = a->tail[n & 1];
   float* tail = a->tail[(n + 1) & 1];
@@ -56,40 +61,56 @@ extern "C" int koe_stream_push(const koe_stream_args* a, int* emitted, void* str
     count_launch();
     KOE_CUDA(cudaGetLastError());
   }
-  const int slot = (int)(n % W);
+  // The tail ends at sample (n + 1) * hop.  The newest frame whose samples are all there is global frame g = n - lag,
+  // lag = n_edge - 1, centred `half` samples into the tail; the frames centred one hop further each are the window-end
+  // variants of the window that ends now: beyond the end of the tail the clip reads as zeros, which is exactly their mask.
+  const int lag = n_edge - 1;
+  const int64_t g = n - lag;
   koe_logmel_args f = {};
   f.audio = tail;
   f.audio_stride = tail_len;
   f.n_clips = S;
   f.n_samples = tail_len;
   f.hop = hop;
-  f.n_frames = 1;
   f.frame_offset = 0;
   f.frame_step = 1;
   f.pad_mode = 0;
-  // F[n] and L[n + 1] are consecutive frames of the tail (centres `half` and `half + hop` = the end of the tail, beyond
-  // which the clip reads as zeros: exactly the "nothing from its centre on" of L), so ONE launch transforms them as one
-  // pair; F goes to the ring slot, L (the pair's second frame) to its own row.  Before the first hop the tail is zeros =
-  // librosa's zero padding.
-  f.n_frames = 2;
   f.sample_offset = half;
   f.lo_rel_hops = KOE_NO_EDGE, f.hi_rel_hops = KOE_NO_EDGE;
-  f.power = a->ring_f + (size_t)slot * KOE_N_MELS, f.power_clip_stride = (int64_t)W * KOE_N_MELS;
-  f.frame_max = a->fmax_f + slot, f.frame_max_clip_stride = W;
-  f.power_b = a->row_l, f.power_b_clip_stride = KOE_N_MELS;
-  f.frame_max_b = a->fmax_l, f.frame_max_b_clip_stride = 1;
+  f.power_clip_stride = (int64_t)W * KOE_N_MELS, f.frame_max_clip_stride = W;
+  f.power_b_clip_stride = KOE_N_MELS, f.frame_max_b_clip_stride = 1;
+  const int slot = (int)(((g % W) + W) % W);
+  // plain frame g (-> ring slot) and the frame one hop later as ONE pair of one launch: at 30 fps that second frame is the
+  // window-end variant L (centred on the tail's end), at 60 fps the last-but-one frame of the window (row_l2)
+  f.n_frames = 2;
+  f.power = a->ring_f + (size_t)slot * KOE_N_MELS, f.frame_max = a->fmax_f + slot;
+  f.power_b = n_edge == 1 ? a->row_l : a->row_l2, f.frame_max_b = n_edge == 1 ? a->fmax_l : a->fmax_l2;
   if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
-  // R[n]: frame n again, nothing before its centre
-  f.n_frames = 1;
-  f.lo_rel_hops = 0;
-  f.power = a->ring_r + (size_t)slot * KOE_N_MELS;
-  f.frame_max = a->fmax_r + slot;
   f.power_b = nullptr, f.frame_max_b = nullptr;
-  if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
-  if (n + 1 < W) return KOE_OK;  // the 8.5 s context is not full yet
+  if (n_edge == 2) {  // the frame centred on the tail's end: the window's last frame
+    f.n_frames = 1;
+    f.frame_offset = 2;
+    f.power = a->row_l, f.power_clip_stride = KOE_N_MELS;
+    f.frame_max = a->fmax_l, f.frame_max_clip_stride = 1;
+    if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+    f.frame_offset = 0;
+    f.power_clip_stride = (int64_t)W * KOE_N_MELS, f.frame_max_clip_stride = W;
+  }
+  // window-start variants of frame g: nothing before its centre (first frame of the window that starts at g), and at
+  // 60 fps nothing before the centre of frame g - 1 (second frame of the window that starts at g - 1)
+  f.n_frames = 1;
+  for (int m = 0; m < n_edge; ++m) {
+    f.lo_rel_hops = -m;
+    f.power = (m == 0 ? a->ring_r : a->ring_r2) + (size_t)slot * KOE_N_MELS;
+    f.frame_max = (m == 0 ? a->fmax_r : a->fmax_r2) + slot;
+    if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+  }
+  if (n + 1 < W) return KOE_OK;  // the context is not full yet
   const int base = (int)((n + 1 - W) % W);  // ring slot of the first frame of the window that ends now
-  if (int rc = koe_dual_stream_ring(a->weights, a->ring_f, a->fmax_f, a->ring_r, a->fmax_r, a->row_l, a->fmax_l, S, W, base,
-                                    W + 1, a->expr_sigmoid, a->out, nullptr, nullptr, a->precision, stream))
+  const float* power[1 + 2 * KOE_MAX_EDGE] = {a->ring_f, a->ring_r, a->row_l, a->ring_r2, a->row_l2};
+  const float* fmax[1 + 2 * KOE_MAX_EDGE] = {a->fmax_f, a->fmax_r, a->fmax_l, a->fmax_r2, a->fmax_l2};
+  if (int rc = koe_dual_stream_ring_edges(a->weights, power, fmax, n_edge, S, W, base, W + 1, a->expr_sigmoid, a->out,
+                                          nullptr, nullptr, a->precision, stream))
     return rc;
   if (a->ema_state != nullptr)
     if (int rc = koe_ema_scan(a->out, S, 1, a->alpha, a->ema_state, a->has_state, stream)) return rc;

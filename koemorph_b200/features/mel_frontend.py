@@ -41,7 +41,7 @@ class LogMelFrontend:
 
     def __init__(self, device, sample_rate: int = 16000, n_fft: int = N_FFT, n_mels: int = N_MELS,
                  f_min: float = 80.0, f_max: float = 8000.0, mel_scale: str = "slaney", window_normalized: bool = False,
-                 log_mode: str = "db", log_eps: float = 0.0):
+                 log_mode: str = "db", log_eps: float = 0.0, win_length: int = 0):
         """``mel_scale`` "slaney" (librosa: Slaney scale, slaney norm) or "htk" (torchaudio default: HTK scale, no norm);
         ``log_mode`` "db" = 10 log10(max(p, 1e-10)) or "ln" = ln(p + log_eps); ``n_fft`` 1024 or 512."""
         device = torch.device(device)
@@ -54,21 +54,23 @@ class LogMelFrontend:
         self._lib = _lib.load()
         cfg = _lib.FrontendConfig(self.device.index, sample_rate, n_fft, n_mels, float(f_min), float(f_max),
                                   1 if mel_scale == "htk" else 0, 0 if mel_scale == "htk" else 1,
-                                  int(bool(window_normalized)), 1 if log_mode == "ln" else 0, float(log_eps))
+                                  int(bool(window_normalized)), 1 if log_mode == "ln" else 0, float(log_eps),
+                                  int(win_length or 0))
         h = C.c_void_p()
         _lib.check(self._lib.koe_frontend_create_ex(C.byref(cfg), C.byref(h)), "koe_frontend_create_ex")
         self._h = h
 
     @classmethod
     def get(cls, device, sample_rate=16000, n_fft=N_FFT, n_mels=N_MELS, f_min=80.0, f_max=8000.0, mel_scale="slaney",
-            window_normalized=False, log_mode="db", log_eps=0.0):
+            window_normalized=False, log_mode="db", log_eps=0.0, win_length=0):
         device = torch.device(device)
         idx = device.index if device.index is not None else torch.cuda.current_device()
+        win_length = 0 if win_length in (None, n_fft) else int(win_length)
         key = (idx, sample_rate, n_fft, n_mels, float(f_min), float(f_max), mel_scale, bool(window_normalized), log_mode,
-               float(log_eps))
+               float(log_eps), win_length)
         if key not in cls._cache:
             cls._cache[key] = cls(torch.device("cuda", idx), sample_rate, n_fft, n_mels, f_min, f_max, mel_scale,
-                                  window_normalized, log_mode, log_eps)
+                                  window_normalized, log_mode, log_eps, win_length)
         return cls._cache[key]
 
     def __del__(self):

@@ -102,13 +102,15 @@ class MelSlidingWindowExtractor:
     """Frame-by-frame log-mel over a sliding 8.5 s context (reference ``:157-412``)."""
 
     def __init__(self, context_window: float = 8.5, update_interval: float = 0.0333, sample_rate: int = 16000,
-                 n_mels: int = 80, n_fft: int = 1024, hop_length: Optional[int] = None,
+                 n_mels: int = 80, n_fft: int = 512, hop_length: Optional[int] = None,
                  win_length: Optional[int] = None, f_min: float = 80.0, f_max: Optional[float] = None,
                  power: float = 2.0, center: bool = True, pad_mode: str = "reflect", device: str = "cuda"):
-        if n_fft != 1024 or n_mels != 80 or (win_length not in (None, n_fft)) or power != 2.0 or not center:
+        if n_fft not in (512, 1024) or n_mels != 80 or power != 2.0 or not center or \
+                (win_length is not None and not 2 <= win_length <= n_fft):
             raise NotImplementedError(
-                "koemorph_b200's frontend kernel is built for n_fft = win_length = 1024, 80 mels, power 2, center=True "
-                "(what SimplifiedDualStreamModel passes, reference simplified_dual_stream_model.py:122-135)")
+                "koemorph_b200's frontend kernel transforms n_fft = 1024 (what SimplifiedDualStreamModel passes, reference "
+                "simplified_dual_stream_model.py:122-135) or 512 (this class's default in the reference, :169), "
+                "win_length <= n_fft, 80 mels, power 2, center=True")
         if pad_mode not in ("reflect", "constant"):
             raise NotImplementedError(f"pad_mode {pad_mode!r}: only 'reflect' and 'constant' are implemented")
         self.context_window, self.update_interval, self.sample_rate = context_window, update_interval, sample_rate
@@ -120,8 +122,8 @@ class MelSlidingWindowExtractor:
         self.hop_length = hop_length or int(sample_rate / target_fps)
         self.win_length = win_length or n_fft
         self.audio_buffer = MelAudioBuffer(context_window, sample_rate, update_interval, self.device)
-        self._fe = LogMelFrontend.get(self.device, sample_rate, n_fft, n_mels, f_min, self.f_max)
-        self.mel_transform = self._fe.filterbank()         # (80, 513) float32, as librosa.filters.mel (:224-230)
+        self._fe = LogMelFrontend.get(self.device, sample_rate, n_fft, n_mels, f_min, self.f_max, win_length=self.win_length)
+        self.mel_transform = self._fe.filterbank()         # (80, 1 + n_fft / 2) float32, as librosa.filters.mel (:224-230)
         self.current_features = None
         self._current_tensor = None
         self.last_update_time = 0

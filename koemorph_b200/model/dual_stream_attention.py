@@ -89,10 +89,29 @@ class DualStreamCrossAttention(nn.Module):
         self._folded.clear()
 
     # ---- folded kernel weights, rebuilt when any parameter (or the compression layer) changes --------------
+    def _weight_slots(self):
+        """(owner dict, name) of every parameter / buffer, in named_parameters() + named_buffers() order.  The module tree
+        is fixed after construction, so the walk is done once; looking the tensors up through the owners' dicts still sees
+        replaced tensors (``.to()``, a new ``nn.Parameter``)."""
+        slots = getattr(self, "_slots", None)
+        if slots is None:
+            slots = []
+            for prefix, mod in self.named_modules():
+                for name in mod._parameters:
+                    slots.append((mod._parameters, name, (prefix + "." if prefix else "") + name))
+            for prefix, mod in self.named_modules():
+                for name in mod._buffers:
+                    if name not in mod._non_persistent_buffers_set:
+                        slots.append((mod._buffers, name, (prefix + "." if prefix else "") + name))
+            self._slots = slots
+        return slots
+
     def kernel_weights(self, compression: Optional[Dict[str, torch.Tensor]] = None) -> CoreWeights:
-        named = list(self.named_parameters()) + list(self.named_buffers())
+        slots = self._weight_slots()
+        slots = [sl for sl in slots if sl[0][sl[1]] is not None]   # (nn.MultiheadAttention registers unused None slots)
+        tensors = [d[n] for d, n, _ in slots]
         comp = [] if compression is None else [compression["weight"], compression["bias"]]
-        key = tuple((t.data_ptr(), t._version, str(t.device)) for _, t in named) + \
+        key = tuple((t.data_ptr(), t._version) for t in tensors) + \
             tuple((t.data_ptr(), t._version) for t in comp) + (self.temperature, self._generation)
         slot = "comp" if compression is not None else "plain"
         hit = self._folded.get(slot)
@@ -101,7 +120,7 @@ class DualStreamCrossAttention(nn.Module):
             if device.type != "cuda":
                 raise RuntimeError(f"DualStreamCrossAttention parameters are on {device}; move the module to a CUDA "
                                    "device (koemorph_b200 has no CPU path)")
-            sd = {k: v for k, v in named}
+            sd = {full: t for (_, _, full), t in zip(slots, tensors)}
             hit = (key, fold(sd, self.num_heads, self.temperature, device, compression, eps=self.mel_norm.eps))
             self._folded[slot] = hit
         return hit[1]

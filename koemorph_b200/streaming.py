@@ -9,7 +9,10 @@ note E; 30 fps geometry, hop 533 >= n_fft / 2):
 * one new "window starts here"  R[n]    the same frame with everything before n*hop zeroed (frame 0 of window n),
 * one "window ends here" frame  L[n+1]  centred on (n+1)*hop with everything from (n+1)*hop on zeroed,
 
-so a step costs 3 FFTs per stream, not 257.  F and R rows go into per-stream rings of ``W`` mel rows in HBM
+so a step costs 3 FFTs per stream, not 257.  At 60 fps (hop 266 < n_fft / 2) two frames per window side are edge
+frames: the newest complete plain frame is F[n-1], and a step adds its two window-start variants R0[n-1] (nothing before
+(n-1)*hop) and R1[n-1] (nothing before (n-2)*hop) plus the last two frames of the window that ends now, L1[n] and
+L0[n+1] -- 5 FFTs per hop against 513.  F and R rows go into per-stream rings of ``W`` mel rows in HBM
 (164 KB per stream), the only audio kept is the last ``n_fft/2 + hop`` samples, and the core kernel addresses the
 rings directly (``koe_dual_stream_ring``).  After the 256th hop every step emits the frame that
 ``SequentialDualStreamModel.forward`` would produce for the window ending at the newest sample, EMA included.
@@ -27,9 +30,6 @@ from . import _lib
 
 class StreamingEngine:
     def __init__(self, model, n_streams: int):
-        if model.hop_length < model.n_fft // 2:
-            raise NotImplementedError("StreamingEngine implements the 30 fps geometry (hop >= n_fft/2, one edge frame "
-                                      "per window side)")
         self.model = model
         self.S = int(n_streams)
         self.dev = next(model.parameters()).device
@@ -39,7 +39,13 @@ class StreamingEngine:
         self.hop = model.hop_length
         self.W = model.mel_sequence_length
         self.half = model.n_fft // 2
-        self.tail_len = self.half + self.hop               # samples [ (n+1)hop - tail_len, (n+1)hop )
+        # frames within n_fft/2 of a window edge see zeros beyond it: one per side at 30 fps (hop 533 >= 512), two at 60 fps
+        # (hop 266): frames 0, 1 and W-1, W of every window are edge variants (SURVEY.md section 8 note E: 5 FFTs per hop)
+        self.n_edge = -(-self.half // self.hop)
+        if self.n_edge > _lib.MAX_EDGE:
+            raise NotImplementedError(f"hop {self.hop} needs {self.n_edge} edge frames per window side (max {_lib.MAX_EDGE})")
+        self.lag = self.n_edge - 1                         # the newest complete plain frame is global frame n - lag
+        self.tail_len = self.half + self.n_edge * self.hop  # samples [ (n+1)hop - tail_len, (n+1)hop )
         f32 = dict(dtype=torch.float32, device=self.dev)
         self._tails = [torch.zeros(self.S, self.tail_len, **f32) for _ in range(2)]   # ping-pong (koe_stream_push)
         self.ring_f = torch.zeros(self.S, self.W, 80, **f32)
@@ -48,6 +54,13 @@ class StreamingEngine:
         self.fmax_r = torch.zeros(self.S, self.W, **f32)
         self.row_l = torch.zeros(self.S, 1, 80, **f32)
         self.fmax_l = torch.zeros(self.S, 1, **f32)
+        if self.n_edge == 2:
+            self.ring_r2 = torch.zeros(self.S, self.W, 80, **f32)
+            self.fmax_r2 = torch.zeros(self.S, self.W, **f32)
+            self.row_l2 = torch.zeros(self.S, 1, 80, **f32)
+            self.fmax_l2 = torch.zeros(self.S, 1, **f32)
+        else:
+            self.ring_r2 = self.fmax_r2 = self.row_l2 = self.fmax_l2 = None
         self.expr = torch.zeros(self.S, **f32)
         self.state = torch.zeros(self.S, 52, **f32)
         self.out = torch.zeros(self.S, 52, **f32)
@@ -59,8 +72,9 @@ class StreamingEngine:
         self.native = True                                  # one koe_stream_push per step (False: call by call from Python)
 
     def reset(self):
-        for t in (*self._tails, self.ring_f, self.ring_r, self.fmax_f, self.fmax_r, self.state):
-            t.zero_()
+        for t in (*self._tails, self.ring_f, self.ring_r, self.fmax_f, self.fmax_r, self.state, self.ring_r2, self.fmax_r2):
+            if t is not None:
+                t.zero_()
         self.n = 0
         self.emitted = 0
         self._args = None                                   # the next step walks the module's weights again
@@ -133,6 +147,9 @@ class StreamingEngine:
         a.ring_f, a.fmax_f = self.ring_f.data_ptr(), self.fmax_f.data_ptr()
         a.ring_r, a.fmax_r = self.ring_r.data_ptr(), self.fmax_r.data_ptr()
         a.row_l, a.fmax_l = self.row_l.data_ptr(), self.fmax_l.data_ptr()
+        if self.n_edge == 2:
+            a.ring_r2, a.fmax_r2 = self.ring_r2.data_ptr(), self.fmax_r2.data_ptr()
+            a.row_l2, a.fmax_l2 = self.row_l2.data_ptr(), self.fmax_l2.data_ptr()
         a.expr_sigmoid, a.out = self.expr.data_ptr(), self.out.data_ptr()
         a.ema_state, a.alpha = (self.state.data_ptr(), self._alpha) if m.use_temporal_smoothing else (None, 1.0)
         a.precision = _lib.PRECISIONS[m.precision]
@@ -146,17 +163,22 @@ class StreamingEngine:
         """The same step issued call by call from Python (``native = False``): the readable statement of what
         koe_stream_push does, kept as its cross-check (tests/test_gpu_streaming.py)."""
         n, hop, W, half = self.n, self.hop, self.W, self.half
-        # slide the audio tail: keep the last n_fft/2 samples, append the hop
+        # slide the audio tail: drop the oldest hop, append the new one
         tail = self._tails[(n + 1) & 1]
         torch.cat([self._tails[n & 1][:, hop:], x], dim=1, out=tail)
-        slot = n % W
+        slot = (n - self.lag) % W                           # ring slot of the newest complete frame g = n - lag
         fe = self._fe
-        # F[n] and L[n+1] are consecutive frames of the tail (L is centred on its end, beyond which the clip reads as
-        # zeros): one launch, F into the ring slot, L (the pair's second frame) into its own row
-        fe.power(tail, hop, 2, sample_offset=half, out=(self.ring_f, self.fmax_f), out_row=slot,
-                 out_b=(self.row_l, self.fmax_l))
-        # R[n]: frame n again, nothing before its centre
+        # frame g and the frame one hop later are consecutive frames of the tail: one launch, g into the ring slot, the
+        # pair's second frame into its own row -- at 30 fps that is L (centred on the tail's end, beyond which the clip
+        # reads as zeros), at 60 fps the last-but-one frame of the window that ends now
+        second = (self.row_l, self.fmax_l) if self.n_edge == 1 else (self.row_l2, self.fmax_l2)
+        fe.power(tail, hop, 2, sample_offset=half, out=(self.ring_f, self.fmax_f), out_row=slot, out_b=second)
+        if self.n_edge == 2:                                # the frame centred on the tail's end: the window's last frame
+            fe.power(tail, hop, 1, frame_offset=2, sample_offset=half, out=(self.row_l, self.fmax_l))
+        # window-start variants of frame g: nothing before its centre; at 60 fps also nothing before frame g-1's centre
         fe.power(tail, hop, 1, sample_offset=half, lo_rel=0, out=(self.ring_r, self.fmax_r), out_row=slot)
+        if self.n_edge == 2:
+            fe.power(tail, hop, 1, sample_offset=half, lo_rel=-1, out=(self.ring_r2, self.fmax_r2), out_row=slot)
         self.n += 1
         if self.n < W:
             return None
@@ -166,11 +188,14 @@ class StreamingEngine:
         lib = _lib.load()
         with torch.cuda.device(self.dev):
             st = _lib.stream_ptr(self.dev)
-            _lib.check(lib.koe_dual_stream_ring(
-                C.byref(w.struct), self.ring_f.data_ptr(), self.fmax_f.data_ptr(), self.ring_r.data_ptr(),
-                self.fmax_r.data_ptr(), self.row_l.data_ptr(), self.fmax_l.data_ptr(), self.S, W, base % W, W + 1,
-                self.expr.data_ptr(), self.out.data_ptr(), None, None, _lib.PRECISIONS[m.precision], st),
-                "koe_dual_stream_ring")
+            bufs = [self.ring_f, self.ring_r, self.row_l] + ([self.ring_r2, self.row_l2] if self.n_edge == 2 else [])
+            fmx = [self.fmax_f, self.fmax_r, self.fmax_l] + ([self.fmax_r2, self.fmax_l2] if self.n_edge == 2 else [])
+            n_buf = 1 + 2 * _lib.MAX_EDGE
+            pw = (C.c_void_p * n_buf)(*[t.data_ptr() for t in bufs] + [None] * (n_buf - len(bufs)))
+            fm = (C.c_void_p * n_buf)(*[t.data_ptr() for t in fmx] + [None] * (n_buf - len(fmx)))
+            _lib.check(lib.koe_dual_stream_ring_edges(
+                C.byref(w.struct), pw, fm, self.n_edge, self.S, W, base % W, W + 1, self.expr.data_ptr(),
+                self.out.data_ptr(), None, None, _lib.PRECISIONS[m.precision], st), "koe_dual_stream_ring_edges")
             if m.use_temporal_smoothing:
                 # sigmoid(smoothing_alpha) is read back once per parameter version, not once per hop (a device sync)
                 ver = (m.smoothing_alpha.data_ptr(), m.smoothing_alpha._version)

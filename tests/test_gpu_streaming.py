@@ -45,9 +45,98 @@ def test_mel_sliding_window_extractor_vs_reference(golden):
     assert ex.process_audio_frame(np.zeros(100, np.float32)) is None      # wrong frame size is refused
     ex.reset()
     assert ex.get_current_features() is None and not ex.audio_buffer.is_full
-    assert create_mel_extractor().n_fft == 1024
+    assert create_mel_extractor().n_fft == 512          # the reference's default (mel_sliding_window.py:169)
     with pytest.raises(NotImplementedError):
-        MelSlidingWindowExtractor(n_fft=512)
+        MelSlidingWindowExtractor(n_fft=2048)
+
+
+def test_mel_sliding_window_extractor_default_geometry_vs_reference():
+    """The reference's DEFAULT constructor (n_fft = win_length = 512, f_max = sr // 2, reflect padding): golden from the
+    unmodified reference class, tests/golden/make_golden_extractor.py."""
+    import os
+    from koemorph_b200.features.mel_sliding_window import MelSlidingWindowExtractor
+    data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extractor_default.npz"))
+    ex = MelSlidingWindowExtractor()
+    assert (ex.n_fft, ex.win_length, ex.f_max, ex.pad_mode, ex.hop_length) == (512, 512, 8000, "reflect", int(data["stft_hop"]))
+    hop = ex.audio_buffer.hop_length
+    assert hop == int(data["hop"])
+    fb = ex.mel_transform
+    assert fb.shape == (80, 257)
+    _close(fb, data["filterbank"], 2e-7 * float(np.abs(data["filterbank"]).max()), "512-point Slaney bank")
+    audio, _ = O.make_inputs(4343, 1, hop * 300, "speechlike")
+    feats = None
+    for i in range(300):
+        ex.last_update_time = 0
+        f = ex.process_audio_frame(audio[0, i * hop:(i + 1) * hop])
+        feats = f if f is not None else feats
+    _close(feats, data["features"], 8e-3, "default-geometry streaming features (dB)")
+    _close(ex.process_audio_batch(audio[0, :100000]), data["batch_features"], 8e-3, "default-geometry batch features (dB)")
+
+
+def test_win_length_shorter_than_n_fft_matches_torch_stft():
+    """win_length < n_fft: the Hann window of win_length points centred in the n_fft frame (librosa pad_center, the same
+    convention as torch.stft, used here as an independent float64 cross-check)."""
+    from koemorph_b200.features.mel_frontend import LogMelFrontend
+    fe = LogMelFrontend.get("cuda", n_fft=1024, win_length=400)
+    audio, _ = O.make_inputs(99, 2, 40000, "speechlike")
+    a = torch.from_numpy(audio).cuda()
+    n_frames = 1 + 40000 // 533
+    db, _ = fe.power(a, 533, n_frames)
+    win = torch.hann_window(400, periodic=True, dtype=torch.float64, device="cuda")
+    S = torch.stft(a.double(), 1024, 533, 400, win, center=True, pad_mode="constant", return_complex=True)
+    mel = torch.einsum("mf,bft->btm", torch.from_numpy(fe.filterbank()).cuda().double(), S.abs() ** 2)[:, :n_frames]
+    ref = 10 * torch.log10(mel.clamp_min(1e-10))
+    big = mel > 1e-6 * mel.amax(dim=(1, 2), keepdim=True)
+    assert (db.double() - ref).abs()[big].max().item() < 1e-3
+
+
+def test_streaming_engine_60fps_matches_sequence_model(golden):
+    """hop 266 < n_fft / 2: two edge frames per window side, five FFTs per hop (SURVEY.md section 8 note E).  Fed hop by
+    hop, the engine reproduces SequentialDualStreamModel.forward at 60 fps -- whose frames are pinned by the reference's
+    golden vector ``seq_60fps`` -- on the native one-call step and on the call-by-call driver, fp32 and bf16."""
+    import koemorph_b200 as K
+    from koemorph_b200.streaming import StreamingEngine
+    cases, data = golden
+    spec = cases["seq_60fps"]
+    w = O.make_weights(spec["wseed"], 60, style=spec["style"])
+    audio, eg = O.make_inputs(spec["iseed"], spec["B"], spec["L"], spec["kind"])
+    m = K.SequentialDualStreamModel(target_fps=60, mel_sequence_length=512).cuda().eval()
+    m.load_state_dict(O.model_state_dict(w), strict=True)
+    m.set_compression_layer(torch.from_numpy(w["compression.weight"]), torch.from_numpy(w["compression.bias"]))
+    a, e = torch.from_numpy(audio).cuda(), torch.from_numpy(eg).cuda()
+    want = torch.from_numpy(data["seq_60fps/blendshapes"])
+    n_hops = spec["L"] // 266
+    assert want.shape[1] == n_hops - 512 + 1
+    for native in (True, False):
+        eng = StreamingEngine(m, spec["B"])
+        assert eng.n_edge == 2 and eng.tail_len == 512 + 2 * 266
+        eng.native = native
+        eng.set_egemaps(e)
+        outs = []
+        for n in range(n_hops):
+            o = eng.step(a[:, n * 266:(n + 1) * 266].contiguous())
+            assert (o is None) == (n < 511)
+            if o is not None:
+                outs.append(o.clone())
+        got = torch.stack(outs, dim=1)
+        _close(got, want, 2e-6, f"60 fps streaming (native={native}) vs the reference's golden frames")
+        _close(got, m(a, egemaps=e)["blendshapes"], 2e-6, "60 fps streaming vs sequence forward")
+        if native:
+            first = got
+        else:
+            assert torch.equal(got, first), "native step and call-by-call driver differ at 60 fps"
+    # ring wrap-around (more than one revolution of the 512-slot rings) and the tensor-core core
+    m.precision = "bf16"
+    eng = StreamingEngine(m, 2)
+    eng.set_egemaps(e.expand(2, -1).contiguous())
+    L2 = (2 * 512 + 7) * 266
+    audio2, _ = O.make_inputs(1234, 2, L2, "speechlike")
+    a2 = torch.from_numpy(audio2).cuda()
+    last = None
+    for n in range(L2 // 266):
+        last = eng.step(a2[:, n * 266:(n + 1) * 266].contiguous())
+    ref2 = m(a2, egemaps=e.expand(2, -1).contiguous())["blendshapes"]
+    _close(last, ref2[:, -1], 1e-4, "60 fps bf16 after ring wrap")
 
 
 def test_streaming_engine_matches_sequence_model():
