@@ -358,6 +358,148 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ---- the per-pair pieces shared by the two kernel organisations below ------------------------------------------------
+// window, first 32-point FFT, twiddles: registers only.  On entry v[bitrev5(n1)] = (a, b)[32 n1 + lane]; on return
+// v[k1] = W_1024^(k1 lane) Y[k1] of column n2 = lane
+__device__ __forceinline__ void fft_first_half(float2 (&v)[32], const float* s_hann, const float2* s_tw, int lane) {
+#pragma unroll
+  for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = __fmul2_rn(v[bitrev5(n1)], bcast(s_hann[32 * n1 + lane]));
+  fft32(v);
+#pragma unroll
+  for (int k1 = 1; k1 < 32; ++k1) {
+    const float2 w = s_tw[k1 * 32 + lane];  // W_1024^(k1 * n2)
+    const float2 z = v[k1];
+    float2 r = __fmul2_rn(z, bcast(w.x));
+    v[k1] = __ffma2_rn(make_float2(-z.y, z.x), bcast(w.y), r);
+  }
+}
+
+// 32x32 transposition through the warp's padded tile, second FFT, separation of the two real spectra: leaves
+// 4 |A_k|^2 at xb[k] and 4 |B_k|^2 at xb[kSecondFrame + k], k = 0..512
+__device__ __forceinline__ void fft_second_half(float2 (&v)[32], float* xb, int lane) {
+  float2* xb2 = reinterpret_cast<float2*>(xb);
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) xb2[k1 * kRowF2 + lane] = v[k1];
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) v[bitrev5(n2)] = xb2[lane * kRowF2 + n2];
+  __syncwarp();
+  fft32(v);  // v[k2] = Z[lane + 32 * k2]
+
+  // separate the two real spectra: partner of k = lane + 32 r is 1024 - k = ((32-lane)&31) + 32 r'.
+  // Lanes 1..31: partner register r' = 31 - r; lane 0: r' = 32 - r, which is the value it fetched (from itself) one
+  // step earlier, and r = 0 is its own partner.  Four steps at a time: only 8 shuffle results are live at once.
+  const int src = (32 - lane) & 31;
+  float* pa = xb;
+  float* pb = xb + kSecondFrame;
+  float2 prev = v[0];
+#pragma unroll
+  for (int r0 = 0; r0 < 16; r0 += 4) {
+    float2 q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[j].x = __shfl_sync(kFullMask, v[31 - r0 - j].x, src);
+      q[j].y = __shfl_sync(kFullMask, v[31 - r0 - j].y, src);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + j;
+      const float2 z = v[r];
+      const float2 c = lane == 0 ? prev : q[j];
+      prev = q[j];
+      // 2A = z + conj(c), 2iB = z - conj(c): (4|A|^2, 4|B|^2) = u*u + w*w, u = (z.x + c.x, z.x - c.x), w = (z.y - c.y, z.y + c.y)
+      const float2 u = __fadd2_rn(bcast(z.x), make_float2(c.x, -c.x));
+      const float2 w = __fadd2_rn(bcast(z.y), make_float2(-c.y, c.y));
+      const float2 pw = __ffma2_rn(w, w, __fmul2_rn(u, u));
+      pa[lane + 32 * r] = pw.x;
+      pb[lane + 32 * r] = pw.y;
+    }
+    asm volatile("" ::: "memory");  // keep the compiler from hoisting the next group's shuffles (register pressure)
+  }
+  if (lane == 0) {  // Nyquist bin 512 = register 16, self-paired: A = z.x, B = z.y (x4 like the others)
+    pa[512] = 4.0f * v[16].x * v[16].x;
+    pb[512] = 4.0f * v[16].y * v[16].y;
+  }
+}
+
+// store phase of one frame pair whose mel rows sit in tile rows (row, row + 1): dB, per-frame maxima, coalesced stores
+template <bool kSplitB>
+__device__ __forceinline__ void store_pair_rows(const FrontendTables& tab, const LogmelParams& p, int clip, int frame,
+                                                bool has_b, const float* tiles, int row, int lane) {
+  const float* tlo = tiles + row * kTileStride;
+  const float* thi = tlo + kSlots * kTileStride;
+  float* dst = p.power + (long long)clip * p.power_clip_stride + (long long)frame * KOE_N_MELS;
+  // the 160 values of the two rows (row B follows row A in the clip's block), five per lane: j = lane + 32 q;
+  // j < 80 -> frame A filter j, else frame B filter j - 80, which sits kTileStride - 80 = 1 float further in the tile
+  float db[5];
+#pragma unroll
+  for (int qd = 0; qd < 5; ++qd) {
+    const int j = lane + 32 * qd;
+    const bool second = qd > 2 || (qd == 2 && lane >= KOE_N_MELS - 64);
+    const int t = j + (second ? kTileStride - KOE_N_MELS : 0);
+    const float pw = tlo[t] + thi[t];
+    // stored in dB (the consumer only subtracts its reference and clamps), or as ln(p + eps) for the torchaudio flavour
+    db[qd] = tab.log_mode == 0 ? db_from_power(pw) : ln_from_power(pw, tab.log_eps);
+  }
+  float mx_a = fmaxf(db[0], db[1]), mx_b = fmaxf(db[3], db[4]);
+  if (lane < KOE_N_MELS - 64) mx_a = fmaxf(mx_a, db[2]); else mx_b = fmaxf(mx_b, db[2]);
+  // row B follows row A, or goes to its own buffer (power_b: pair j of the clip -> row j there); dst_b is biased by
+  // one row so that the same indices address it
+  float* dst_b = dst;
+  if constexpr (kSplitB)
+    dst_b = p.power_b + (long long)clip * p.power_b_clip_stride + (long long)(frame >> 1) * KOE_N_MELS - KOE_N_MELS;
+  dst[lane] = db[0];
+  dst[lane + 32] = db[1];
+  float* dst_mid = lane < KOE_N_MELS - 64 ? dst : dst_b;  // the third 32-value piece straddles the two rows
+  if (has_b || lane < KOE_N_MELS - 64) dst_mid[lane + 64] = db[2];
+  if (has_b) {
+    dst_b[lane + 96] = db[3];
+    dst_b[lane + 128] = db[4];
+  }
+  if (p.frame_max != nullptr) {
+    const int ia = __reduce_max_sync(kFullMask, float_order(mx_a));
+    const int ib = __reduce_max_sync(kFullMask, float_order(mx_b));
+    float* fm = p.frame_max + (long long)clip * p.fmax_clip_stride + frame;
+    float* fm_b = fm;
+    if constexpr (kSplitB) fm_b = p.frame_max_b + (long long)clip * p.fmax_b_clip_stride + (frame >> 1) - 1;
+    if (lane == 0) fm[0] = order_float(ia);
+    if (lane == 1 && has_b) fm_b[1] = order_float(ib);
+  }
+}
+
+// Pair of iteration `iter` (pairs iter * kWarps + warp) for one warp.  Interior pairs (all but the few per clip that touch
+// an edge) come last in the launch order, clip by clip; successive calls advance by a constant number of pairs
+// (gridDim.x * kWarps), so clip and pair are kept incrementally: no division in the loop.
+struct PairLocator {
+  int in_clip = -1, in_j = 0;  // interior position of the pair located last (-1: none yet)
+  __device__ __forceinline__ PairInfo locate(const LogmelParams& p, unsigned iter, unsigned n_iters, unsigned total_pairs,
+                                             unsigned ppc, int warp) {
+    const unsigned n_edge_pairs = p.mid_pairs > 0 ? (unsigned)p.n_clips * (unsigned)(p.edge_lo + p.edge_hi) : total_pairs;
+    const unsigned pair = iter < n_iters ? iter * kWarps + warp : total_pairs;
+    if (pair < n_edge_pairs || pair >= total_pairs) {
+      in_clip = -1;
+      return locate_pair(p, pair, total_pairs, ppc);
+    }
+    if (in_clip < 0) {
+      const unsigned r = pair - n_edge_pairs;
+      in_clip = (int)(r / (unsigned)p.mid_pairs);
+      in_j = (int)(r - (unsigned)in_clip * (unsigned)p.mid_pairs);
+    } else {
+      in_clip += p.step_clips;
+      in_j += p.step_pairs;
+      if (in_j >= p.mid_pairs) in_j -= p.mid_pairs, ++in_clip;
+    }
+    PairInfo pi;
+    pi.clip = in_clip;
+    pi.frame = 2 * (p.edge_lo + in_j);
+    pi.has_b = true;
+    pi.interior = true;
+    pi.fa_lo = p.sample_offset + (p.frame_offset + pi.frame * p.frame_step) * p.hop - kFrameLen / 2;
+    pi.fb_lo = pi.fa_lo + p.frame_step * p.hop;
+    return pi;
+  }
+};
+
 // kSplitB: the pairs' second frames go to their own buffer (LogmelParams::power_b; the streaming step) -- a separate
 // instantiation so that the batch kernel carries none of it (the extra pointer arithmetic cost it 3 us of 179)
 //
@@ -381,8 +523,8 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   float2* s_binw = s_tw + 1024;                                    // kMaxBins float2
   int4* s_groups = reinterpret_cast<int4*>(s_binw + kMaxBins);     // kMaxGroups
   int* s_runs = reinterpret_cast<int*>(s_groups + kMaxGroups);     // kWarps + 1 (+ pad to 32)
-  float* s_tiles = reinterpret_cast<float*>(s_runs + 32);          // 2 buffers x (tlo | thi), each kSlots * kTileStride
-  float* s_scratch = s_tiles + 4 * kSlots * kTileStride;           // kWarps * kScratch, 16-byte aligned, bank 0
+  float* s_tiles = reinterpret_cast<float*>(s_runs + 32);          // (tlo | thi), each kSlots * kTileStride
+  float* s_scratch = s_tiles + 2 * kSlots * kTileStride;           // kWarps * kScratch, 16-byte aligned, bank 0
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scratch + kWarps * kScratch);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -396,7 +538,7 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   for (int i = tid; i < tab.n_groups; i += kThreads) s_groups[i] = tab.groups[i];
   if (tid <= kWarps) s_runs[tid] = tab.runs[tid];
   // cells that no group writes (filter 0's rising half; filters without a falling / rising group in sparse banks) stay 0
-  for (int i = tid; i < 4 * kSlots * kTileStride; i += kThreads) s_tiles[i] = 0.0f;
+  for (int i = tid; i < 2 * kSlots * kTileStride; i += kThreads) s_tiles[i] = 0.0f;
   const uint32_t mel_done = smem_addr(s_bar);
   if (tid == 0) {
     bar_init(mel_done, kWarps);
@@ -408,81 +550,13 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   const unsigned total_pairs = (unsigned)p.n_clips * ppc;
   const unsigned n_iters = (total_pairs + kWarps - 1) / kWarps;
   float* xb = s_scratch + warp * kScratch;
-  float2* xb2 = reinterpret_cast<float2*>(xb);
   const int order = (p.store_order >> (2 * (warp >> 2))) & 3;  // 0: S before F; 1: S after L; 2: S between T and L
 
-  // store phase of one frame pair: warp w owns slots 2w, 2w+1 of the mel tiles
-  auto store_rows = [&](int clip, int frame, bool has_b, const float* tiles) {
-      const float* tlo = tiles + (2 * warp) * kTileStride;
-      const float* thi = tlo + kSlots * kTileStride;
-      float* dst = p.power + (long long)clip * p.power_clip_stride + (long long)frame * KOE_N_MELS;
-      // the 160 values of the two rows (row B follows row A in the clip's block), five per lane: j = lane + 32 q;
-      // j < 80 -> frame A filter j, else frame B filter j - 80, which sits kTileStride - 80 = 1 float further in the tile
-      float db[5];
-#pragma unroll
-      for (int qd = 0; qd < 5; ++qd) {
-        const int j = lane + 32 * qd;
-        const bool second = qd > 2 || (qd == 2 && lane >= KOE_N_MELS - 64);
-        const int t = j + (second ? kTileStride - KOE_N_MELS : 0);
-        const float pw = tlo[t] + thi[t];
-        // stored in dB (the consumer only subtracts its reference and clamps), or as ln(p + eps) for the torchaudio flavour
-        db[qd] = tab.log_mode == 0 ? db_from_power(pw) : ln_from_power(pw, tab.log_eps);
-      }
-      float mx_a = fmaxf(db[0], db[1]), mx_b = fmaxf(db[3], db[4]);
-      if (lane < KOE_N_MELS - 64) mx_a = fmaxf(mx_a, db[2]); else mx_b = fmaxf(mx_b, db[2]);
-      // row B follows row A, or goes to its own buffer (power_b: pair j of the clip -> row j there); dst_b is biased by
-      // one row so that the same indices address it
-      float* dst_b = dst;
-      if constexpr (kSplitB)
-        dst_b = p.power_b + (long long)clip * p.power_b_clip_stride + (long long)(frame >> 1) * KOE_N_MELS - KOE_N_MELS;
-      dst[lane] = db[0];
-      dst[lane + 32] = db[1];
-      float* dst_mid = lane < KOE_N_MELS - 64 ? dst : dst_b;  // the third 32-value piece straddles the two rows
-      if (has_b || lane < KOE_N_MELS - 64) dst_mid[lane + 64] = db[2];
-      if (has_b) {
-        dst_b[lane + 96] = db[3];
-        dst_b[lane + 128] = db[4];
-      }
-      if (p.frame_max != nullptr) {
-        const int ia = __reduce_max_sync(kFullMask, float_order(mx_a));
-        const int ib = __reduce_max_sync(kFullMask, float_order(mx_b));
-        float* fm = p.frame_max + (long long)clip * p.fmax_clip_stride + frame;
-        float* fm_b = fm;
-        if constexpr (kSplitB) fm_b = p.frame_max_b + (long long)clip * p.fmax_b_clip_stride + (frame >> 1) - 1;
-        if (lane == 0) fm[0] = order_float(ia);
-        if (lane == 1 && has_b) fm_b[1] = order_float(ib);
-      }
+  auto store_rows = [&](int clip, int frame, bool has_b, const float* tiles) {  // warp w owns tile rows 2w, 2w + 1
+    store_pair_rows<kSplitB>(tab, p, clip, frame, has_b, tiles, 2 * warp, lane);
   };
-
-  // Pair of iteration `it` for this warp.  Interior pairs (all but the few per clip that touch an edge) come last in the
-  // launch order, clip by clip; their position advances by a constant number of pairs per iteration, so clip and pair
-  // are kept incrementally (no division in the loop).
-  const unsigned n_edge_pairs = p.mid_pairs > 0 ? (unsigned)p.n_clips * (unsigned)(p.edge_lo + p.edge_hi) : total_pairs;
-  int in_clip = -1, in_j = 0;  // interior position of the pair located last (-1: none yet)
-  auto locate = [&](unsigned iter) -> PairInfo {
-    const unsigned pair = iter < n_iters ? iter * kWarps + warp : total_pairs;
-    if (pair < n_edge_pairs || pair >= total_pairs) {
-      in_clip = -1;
-      return locate_pair(p, pair, total_pairs, ppc);
-    }
-    if (in_clip < 0) {
-      const unsigned r = pair - n_edge_pairs;
-      in_clip = (int)(r / (unsigned)p.mid_pairs);
-      in_j = (int)(r - (unsigned)in_clip * (unsigned)p.mid_pairs);
-    } else {
-      in_clip += p.step_clips;
-      in_j += p.step_pairs;
-      if (in_j >= p.mid_pairs) in_j -= p.mid_pairs, ++in_clip;
-    }
-    PairInfo pi;
-    pi.clip = in_clip;
-    pi.frame = 2 * (p.edge_lo + in_j);
-    pi.has_b = true;
-    pi.interior = true;
-    pi.fa_lo = p.sample_offset + (p.frame_offset + pi.frame * p.frame_step) * p.hop - kFrameLen / 2;
-    pi.fb_lo = pi.fa_lo + p.frame_step * p.hop;
-    return pi;
-  };
+  PairLocator loc;
+  auto locate = [&](unsigned iter) { return loc.locate(p, iter, n_iters, total_pairs, ppc, warp); };
 
   float2 v[32];
   unsigned it = blockIdx.x;
@@ -494,7 +568,9 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   unsigned k = 0;                      // iterations done by this CTA: parity of the mbarrier phase / tile buffer
 
   for (; it < n_iters; it += gridDim.x, ++k) {
-    const float* prev_tiles = s_tiles + ((k + 1) & 1) * (2 * kSlots * kTileStride);
+    // the mel tiles hold the previous iteration's rows until the next mel phase, i.e. until the __syncthreads below:
+    // every store phase, early or late, comes before it
+    const float* prev_tiles = s_tiles;
     if (order == 0 && pend_frame >= 0) {
       bar_wait(mel_done, (k + 1) & 1);  // the previous mel phase, by every warp
       store_rows(pend_clip, pend_frame, pend_has_b, prev_tiles);
@@ -502,65 +578,10 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
     }
     // ------------------------------------------------------------------ FFT phase (per warp)
     const PairInfo cur = nxt;
-    if (cur.frame >= 0) {
-#pragma unroll
-      for (int n1 = 0; n1 < 32; ++n1) v[bitrev5(n1)] = __fmul2_rn(v[bitrev5(n1)], bcast(s_hann[32 * n1 + lane]));
-      fft32(v);  // v[k1] = Y[k1] of column n2 = lane
-#pragma unroll
-      for (int k1 = 1; k1 < 32; ++k1) {
-        const float2 w = s_tw[k1 * 32 + lane];  // W_1024^(k1 * n2)
-        const float2 z = v[k1];
-        float2 r = __fmul2_rn(z, bcast(w.x));
-        v[k1] = __ffma2_rn(make_float2(-z.y, z.x), bcast(w.y), r);
-      }
-    }
+    if (cur.frame >= 0) fft_first_half(v, s_hann, s_tw, lane);
     // the tile still holds this warp's spectra of the previous iteration until every warp has finished that mel phase
     if (k > 0) bar_wait(mel_done, (k + 1) & 1);
-    if (cur.frame >= 0) {
-      // 32x32 transpose of complex values through the warp's padded tile
-#pragma unroll
-      for (int k1 = 0; k1 < 32; ++k1) xb2[k1 * kRowF2 + lane] = v[k1];
-      __syncwarp();
-#pragma unroll
-      for (int n2 = 0; n2 < 32; ++n2) v[bitrev5(n2)] = xb2[lane * kRowF2 + n2];
-      __syncwarp();
-      fft32(v);  // v[k2] = Z[lane + 32 * k2]
-
-      // separate the two real spectra: partner of k = lane + 32 r is 1024 - k = ((32-lane)&31) + 32 r'.
-      // Lanes 1..31: partner register r' = 31 - r; lane 0: r' = 32 - r, which is the value it fetched (from itself) one
-      // step earlier, and r = 0 is its own partner.  Four steps at a time: only 8 shuffle results are live at once.
-      const int src = (32 - lane) & 31;
-      float* pa = xb;
-      float* pb = xb + kSecondFrame;
-      float2 prev = v[0];
-#pragma unroll
-      for (int r0 = 0; r0 < 16; r0 += 4) {
-        float2 q[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          q[j].x = __shfl_sync(kFullMask, v[31 - r0 - j].x, src);
-          q[j].y = __shfl_sync(kFullMask, v[31 - r0 - j].y, src);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = r0 + j;
-          const float2 z = v[r];
-          const float2 c = lane == 0 ? prev : q[j];
-          prev = q[j];
-          // 2A = z + conj(c), 2iB = z - conj(c): (4|A|^2, 4|B|^2) = u*u + w*w, u = (z.x + c.x, z.x - c.x), w = (z.y - c.y, z.y + c.y)
-          const float2 u = __fadd2_rn(bcast(z.x), make_float2(c.x, -c.x));
-          const float2 w = __fadd2_rn(bcast(z.y), make_float2(-c.y, c.y));
-          const float2 pw = __ffma2_rn(w, w, __fmul2_rn(u, u));
-          pa[lane + 32 * r] = pw.x;
-          pb[lane + 32 * r] = pw.y;
-        }
-        asm volatile("" ::: "memory");  // keep the compiler from hoisting the next group's shuffles (register pressure)
-      }
-      if (lane == 0) {  // Nyquist bin 512 = register 16, self-paired: A = z.x, B = z.y (x4 like the others)
-        pa[512] = 4.0f * v[16].x * v[16].x;
-        pb[512] = 4.0f * v[16].y * v[16].y;
-      }
-    }
+    if (cur.frame >= 0) fft_second_half(v, xb, lane);
     if (order == 2 && pend_frame >= 0) {
       store_rows(pend_clip, pend_frame, pend_has_b, prev_tiles);
       pend_frame = -1;
@@ -581,7 +602,7 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
 
     // ------------------------------------------------------------------ mel phase: lane = frame slot, warp = run of bins
     {
-      float* tlo = s_tiles + (k & 1) * (2 * kSlots * kTileStride) + lane * kTileStride;
+      float* tlo = s_tiles + lane * kTileStride;
       float* thi = tlo + kSlots * kTileStride;
       const float* spec = s_scratch + (lane >> 1) * kScratch + (lane & 1) * kSecondFrame;
       if (kDefaultBank)
@@ -595,13 +616,110 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   }
   if (pend_frame >= 0) {
     bar_wait(mel_done, (k + 1) & 1);
-    store_rows(pend_clip, pend_frame, pend_has_b, s_tiles + ((k + 1) & 1) * (2 * kSlots * kTileStride));
+    store_rows(pend_clip, pend_frame, pend_has_b, s_tiles);
   }
 }
 
+// ---- warp-specialised organisation (default bank, batch launches) ------------------------------------------------------
+// 16 producer warps (one frame pair each per iteration: loads, FFT, spectra into their tile) never touch the mel or store
+// phases and never meet at a CTA barrier; 8 consumer warps (two per scheduler) run the mel phase of iteration k -- lane =
+// frame, two runs of bins each -- and the store phase while the producers are already in iteration k + 1.  The register
+// file is split with setmaxnreg: launch at 80 registers x 768 threads, producers grow (to 96), consumers shrink (to 48).
+// Handshakes (mbarriers): spec_ready (16 producer arrivals: the 32 spectra and pair descriptors of iteration k are in
+// shared memory), spec_free (8 consumer arrivals: nobody reads the spectra of iteration k any more, the producers may
+// overwrite their tiles with the next transposition); the consumers meet at a named barrier between mel and store phase.
+constexpr int kWsProducers = kWarps;
+constexpr int ws_launch_regs(int consumers) { return (65536 / ((kWsProducers + consumers) * 32)) & ~7; }
+
+template <int kWsConsumers, int kWsProducerRegs, int kWsConsumerRegs>
+__global__ void __launch_bounds__((kWsProducers + kWsConsumers) * 32, 1)
+logmel_power_ws_kernel(FrontendTables tab, LogmelParams p) {
+  constexpr int kWsThreads = (kWsProducers + kWsConsumers) * 32;
+  static_assert(kWsProducers * kWsProducerRegs + kWsConsumers * kWsConsumerRegs <=
+                    (kWsProducers + kWsConsumers) * ws_launch_regs(kWsConsumers),
+                "setmaxnreg redistributes the launch allocation");
+  static_assert(kWarps % kWsConsumers == 0, "whole runs per consumer");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_hann = reinterpret_cast<float*>(smem_raw);              // 1024
+  float2* s_tw = reinterpret_cast<float2*>(s_hann + kFrameLen);    // 1024 float2
+  float* s_tiles = reinterpret_cast<float*>(s_tw + 1024);          // 2 buffers x (tlo | thi), each kSlots * kTileStride
+  float* s_scratch = s_tiles + 4 * kSlots * kTileStride;           // kWarps * kScratch, 16-byte aligned
+  int4* s_pair = reinterpret_cast<int4*>(s_scratch + kWarps * kScratch);  // [2][kWarps] {clip, frame, has_b, -}
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pair + 2 * kWarps);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  for (int i = tid; i < kFrameLen; i += kWsThreads) s_hann[i] = tab.hann[i];
+  for (int i = tid; i < 1024; i += kWsThreads) s_tw[i] = tab.tw[i];
+  for (int i = tid; i < 4 * kSlots * kTileStride; i += kWsThreads) s_tiles[i] = 0.0f;
+  const uint32_t spec_ready = smem_addr(s_bar), spec_free = smem_addr(s_bar + 1);
+  if (tid == 0) {
+    bar_init(spec_ready, kWsProducers);
+    bar_init(spec_free, kWsConsumers);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const unsigned ppc = (unsigned)(p.n_frames + 1) >> 1;
+  const unsigned total_pairs = (unsigned)p.n_clips * ppc;
+  const unsigned n_iters = (total_pairs + kWarps - 1) / kWarps;
+  const unsigned first = blockIdx.x, stride = gridDim.x;
+  const unsigned n_local = first < n_iters ? (n_iters - first + stride - 1) / stride : 0;
+
+  if (warp < kWsProducers) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsProducerRegs));
+    float* xb = s_scratch + warp * kScratch;
+    PairLocator loc;
+    float2 v[32];
+    PairInfo nxt = loc.locate(p, first, n_iters, total_pairs, ppc, warp);
+    if (nxt.interior) load_interior(p, nxt, lane, v);
+    else if (nxt.frame >= 0) load_edge(p, nxt, lane, v);
+    for (unsigned k = 0; k < n_local; ++k) {
+      const PairInfo cur = nxt;
+      if (cur.frame >= 0) fft_first_half(v, s_hann, s_tw, lane);
+      // the tile holds this warp's spectra of iteration k - 1 until every consumer has finished that mel phase
+      if (k > 0) bar_wait(spec_free, (k + 1) & 1);
+      if (cur.frame >= 0) fft_second_half(v, xb, lane);
+      if (lane == 0) s_pair[(k & 1) * kWarps + warp] = make_int4(cur.clip, cur.frame, cur.has_b ? 1 : 0, 0);
+      __syncwarp();
+      if (lane == 0) bar_arrive(spec_ready);
+      // audio of the next iteration (an L2 prefetch of these lines one iteration ahead changed nothing: 146.7 vs 146.3 us)
+      nxt = loc.locate(p, k + 1 < n_local ? first + (k + 1) * stride : n_iters, n_iters, total_pairs, ppc, warp);
+      if (nxt.interior) load_interior(p, nxt, lane, v);
+      else if (nxt.frame >= 0) load_edge(p, nxt, lane, v);
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsConsumerRegs));
+    const int c = warp - kWsProducers;
+    for (unsigned k = 0; k < n_local; ++k) {
+      float* tiles = s_tiles + (k & 1) * (2 * kSlots * kTileStride);
+      bar_wait(spec_ready, k & 1);
+      {
+        float* tlo = tiles + lane * kTileStride;
+        float* thi = tlo + kSlots * kTileStride;
+        const float* spec = s_scratch + (lane >> 1) * kScratch + (lane & 1) * kSecondFrame;
+#pragma unroll 1
+        for (int run = c * (kWarps / kWsConsumers); run < (c + 1) * (kWarps / kWsConsumers); ++run)
+          mel_phase_default(run, spec, tlo, thi);
+      }
+      __syncwarp();
+      if (lane == 0) bar_arrive(spec_free);
+      asm volatile("bar.sync 1, %0;" ::"n"(kWsConsumers * 32) : "memory");  // every run of this iteration is in the tiles
+#pragma unroll 1
+      for (int w = c * (kWarps / kWsConsumers); w < (c + 1) * (kWarps / kWsConsumers); ++w) {
+        const int4 pi = s_pair[(k & 1) * kWarps + w];
+        if (pi.y >= 0) store_pair_rows<false>(tab, p, pi.x, pi.y, pi.z != 0, tiles, 2 * w, lane);
+      }
+    }
+  }
+}
+
+constexpr size_t kLogmelWsSmem = sizeof(float) * kFrameLen + sizeof(float2) * 1024 +
+                                 sizeof(float) * (4 * kSlots * kTileStride + kWarps * kScratch) + sizeof(int4) * 2 * kWarps + 16;
+
 constexpr size_t kLogmelSmem = sizeof(float) * kFrameLen + sizeof(float2) * 1024 + sizeof(float2) * kMaxBins +
                                sizeof(int4) * kMaxGroups + sizeof(int) * 32 +
-                               sizeof(float) * (4 * kSlots * kTileStride + kWarps * kScratch) + 16;
+                               sizeof(float) * (2 * kSlots * kTileStride + kWarps * kScratch) + 16;
 
 // ---- dB normalisation: ref = clip max, clamp, rescale; emits long-term and last-3 short-term features
 __global__ void logmel_normalise_kernel(const float* __restrict__ power, const float* __restrict__ frame_max,
@@ -905,6 +1023,8 @@ extern "C" int koe_frontend_create_ex(const koe_frontend_config* cfg, koe_fronte
     e = cudaFuncSetAttribute(logmel_power_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelSmem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(logmel_power_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(logmel_power_ws_kernel<8, 96, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLogmelWsSmem);
   cudaDeviceProp prop;
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) {
@@ -941,8 +1061,10 @@ extern "C" int koe_frontend_filterbank_host(const koe_frontend_t* fe, float* fb_
 
 // experiment switch of the log-mel kernel (scripts/k1_variants.py): placement of the store phase per warp class
 static int g_k1_store_order = 0x44;  // classes 0, 2: before the FFT; classes 1, 3: after the next pair's loads
-extern "C" int koe_debug_k1_variant(int store_order) {
+static int g_k1_warp_specialised = 1;
+extern "C" int koe_debug_k1_variant(int store_order, int warp_specialised) {
   g_k1_store_order = store_order;
+  g_k1_warp_specialised = warp_specialised;
   return KOE_OK;
 }
 
@@ -1024,7 +1146,9 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
       logmel_power_kernel<true, true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
     else
       logmel_power_kernel<false, true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
-  } else if (fe->default_bank)
+  } else if (fe->default_bank && g_k1_warp_specialised == 1)
+    logmel_power_ws_kernel<8, 96, 48><<<grid, (kWsProducers + 8) * 32, kLogmelWsSmem, (cudaStream_t)stream>>>(tab, p);
+  else if (fe->default_bank)
     logmel_power_kernel<true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
   else
     logmel_power_kernel<false><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);

@@ -26,11 +26,11 @@ audio[2] = 0.5 * torch.sin(2 * torch.pi * 440.0 * t)
 audio[3, :70000] = 0
 fe = LogMelFrontend.get("cuda")
 lib = _lib.load()
-lib.koe_debug_k1_variant.argtypes = [__import__("ctypes").c_int]
+lib.koe_debug_k1_variant.argtypes = [__import__("ctypes").c_int] * 2
 
 
-def set_variant(order):
-    rc = lib.koe_debug_k1_variant(order)
+def set_variant(order, ws=0):
+    rc = lib.koe_debug_k1_variant(order, ws)
     assert rc == 0, lib.koe_last_error()
 
 
@@ -61,9 +61,10 @@ variants = [("all store-first 0x00", 0x00), ("all after-loads 0x55", 0x55), ("al
             ("classes 1,3 after-loads 0x44", 0x44), ("classes 2,3 after-loads 0x50", 0x50),
             ("classes 1,3 after-fft 0x88", 0x88), ("0,1,2,1 -> 0x64", 0x64), ("class 3 after-loads 0x40", 0x40)]
 
+variants = [(n, o, 0) for n, o in variants[:4]] + [("warp-specialised: 16 producers @96 regs + 8 consumers @48 regs (shipped)", 0, 1)]
 out = (torch.empty_like(ref_db), torch.empty_like(ref_fm))
-for name, order in variants:
-    set_variant(order)
+for name, order, ws in variants:
+    set_variant(order, ws)
     out[0].fill_(float("nan"))
     out[1].fill_(float("nan"))
     fe.power(audio, hop, n_frames, out=out)
@@ -72,10 +73,10 @@ for name, order in variants:
     med, mn = timed(out)
     print(f"{name:36s} median {med:7.1f} us  min {mn:7.1f} us  bit-identical {same}", flush=True)
     assert same, name
-set_variant(0x44)
+set_variant(0x44, 1)
 
 # timing probe (results are not written): FFT + loads only, no CTA barrier / mel phase / store phase
 set_variant(0x100)
 med, mn = timed(out)
 print(f"{'probe: FFT + loads only, free running':36s} median {med:7.1f} us  min {mn:7.1f} us")
-set_variant(0x44)
+set_variant(0x44, 1)
