@@ -35,7 +35,8 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    # everything a source may include: headers and the generated tables (melbank_default.inc)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     headers.append(os.path.join(os.path.dirname(CSRC), "..", "include", "koemorph_b200.h"))
     objs = []
     for src in SOURCES:
