@@ -500,6 +500,26 @@ struct PairLocator {
   }
 };
 
+// the same for a warp that expects to wait long (the consumers of the warp-specialised kernel wait for the producers most
+// of the time): try_wait with a suspend-time hint, then sleep between polls -- a tight poll loop issued 30 % of all the
+// kernel's instructions (ncu: BRA / SYNCS / YIELD / ISETP), taking issue slots from the producers on the same scheduler
+__device__ __forceinline__ void bar_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    if (!ok) {
+      __nanosleep(128);
+      if (spin > (1u << 20)) __trap();
+    }
+  }
+}
+
 // kSplitB: the pairs' second frames go to their own buffer (LogmelParams::power_b; the streaming step) -- a separate
 // instantiation so that the batch kernel carries none of it (the extra pointer arithmetic cost it 3 us of 179)
 //
@@ -693,7 +713,7 @@ logmel_power_ws_kernel(FrontendTables tab, LogmelParams p) {
     const int c = warp - kWsProducers;
     for (unsigned k = 0; k < n_local; ++k) {
       float* tiles = s_tiles + (k & 1) * (2 * kSlots * kTileStride);
-      bar_wait(spec_ready, k & 1);
+      bar_wait_parked(spec_ready, k & 1);
       {
         float* tlo = tiles + lane * kTileStride;
         float* thi = tlo + kSlots * kTileStride;
