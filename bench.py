@@ -173,9 +173,8 @@ def run_reference(args):
     kind = _cpu_kind()
     clips_per_worker = 4
     pool, cores = _cpu_pool(clips_per_worker, kind)
-    # one step = a bounded sample of the GPU arm's step: every worker forwards its 4 clips `reps` times, ~512 clips in all
-    # for the port; the unmodified reference is ~4x slower per clip, so its step is one pass (64 clips on 16 cores)
-    reps = max(1, -(-CLIPS_PER_GPU // (cores * clips_per_worker))) if kind == "port" else 1
+    # one step = the GPU arm's step: every worker forwards its 4 clips `reps` times, ~512 clips in all
+    reps = max(1, -(-CLIPS_PER_GPU // (cores * clips_per_worker)))
     times = []
     with pool:
         for i in range(args.warmup + args.steps):
