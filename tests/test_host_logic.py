@@ -137,7 +137,8 @@ def test_ctypes_mirrors_have_the_size_of_the_c_structs():
     import ctypes as C
     from koemorph_b200 import _lib
     lib = _lib.load()
-    for which, mirror in enumerate((_lib.FrontendConfig, _lib.LogmelArgs, _lib.CoreWeightsStruct, _lib.StreamArgs)):
+    for which, mirror in enumerate((_lib.FrontendConfig, _lib.LogmelArgs, _lib.CoreWeightsStruct, _lib.StreamArgs,
+                                    _lib.ForwardArgs)):
         assert lib.koe_sizeof_struct(which) == C.sizeof(mirror), mirror.__name__
     assert lib.koe_sizeof_struct(99) == -1
 
