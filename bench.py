@@ -30,6 +30,9 @@ CLIP_SECONDS = 8.5
 METRIC = "audio-seconds/sec (30fps, 8.5s ctx)"
 UNIT = "audio-s/s"
 WORKLOAD = "512 x 8.5 s clips @16 kHz per GPU, 30 fps, 256x80 mel context, 1 frame/clip (BASELINE.json configs[1])"
+# the same dict in both arms' lines; "l2": how the GPU arm keeps its timed iterations cache-cold
+CONFIG = {"workload": WORKLOAD, "clips_per_step_per_gpu": CLIPS_PER_GPU,
+          "l2": "inputs 278.5 MB per GPU > 126 MB L2, no flush needed"}
 
 
 # ----------------------------------------------------------------------------- CPU arm: the reference's own forward
@@ -189,7 +192,8 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "step_sample": f"{n} clips per step"},
+            "config": dict(CONFIG),
+            "details": {"step_sample": f"{n} clips per step"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -512,11 +516,13 @@ def run_gpu(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "bf16": "bf16"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clips_per_gpu": B, "parallelism": f"clip-shard x{world}",
-                       "precision": args.precision, "timed_call": "SequentialDualStreamModel.forward(audio, egemaps=, out=)",
-                       "collective": f"one all_gather of the ({K_steps},B,1,52) results at the end of the timed region; "
-                                     "start events behind a device-side rendezvous (tiny all-reduce)" if world > 1 else "none",
-                       "l2": "inputs 278.5 MB per GPU > 126 MB L2, no flush needed"},
+            # (the same dict as the reference arm's, so that the two lines compare as the same configuration)
+            "config": dict(CONFIG),
+            "details": {"parallelism": f"clip-shard x{world}", "precision": args.precision,
+                        "timed_call": "SequentialDualStreamModel.forward(audio, egemaps=, out=)",
+                        "collective": f"one all_gather of the ({K_steps},B,1,52) results at the end of the timed region; "
+                                      "start events behind a device-side rendezvous (tiny all-reduce)" if world > 1 else "none",
+                        },
             "clocks": clocks,
             "ranks": rank_stats,
             "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT},
