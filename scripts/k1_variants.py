@@ -80,3 +80,10 @@ set_variant(0x100)
 med, mn = timed(out)
 print(f"{'probe: FFT + loads only, free running':36s} median {med:7.1f} us  min {mn:7.1f} us")
 set_variant(0x44, 1)
+
+# timing probe: the warp-specialised kernel with the producers NOT waiting for the consumers (results invalid): what full
+# decoupling of producers and consumers could buy at most
+set_variant(0x200, 1)
+med, mn = timed(out)
+print(f"{'probe: ws kernel, producers never wait for the consumers':60s} median {med:7.1f} us  min {mn:7.1f} us")
+set_variant(0x44, 1)
