@@ -299,6 +299,13 @@ def test_bf16_tensor_path_full_batch_consistency(K):
     perm = torch.randperm(512, device="cuda", generator=g)
     out_p = m(audio[perm].contiguous(), egemaps=eg[perm].contiguous())["blendshapes"]
     assert torch.equal(out_p, out[perm])
+    # ... and against the CPU oracle on clips spread over the batch (first / last CTA round, middle): the full-size run is
+    # checked by something other than the repo's own kernels
+    w = O.make_weights(spec["wseed"], 30, style=spec["style"])
+    pick = [0, 1, 147, 148, 295, 444, 510, 511]
+    want = O.forward_sequence(w, audio[pick].cpu().numpy(), eg[pick].cpu().numpy())["blendshapes"]
+    _close(ref[pick], want, 0, OUT_ATOL, "fp32 kernel at batch 512 vs oracle")
+    _close(out[pick], want, 0, BF16_OUT_ATOL, "bf16 kernel at batch 512 vs oracle")
 
 
 def test_bf16_unsupported_geometry_is_refused_not_faked(K):
