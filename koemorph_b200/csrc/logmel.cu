@@ -14,15 +14,17 @@
 //   * after the second pass lane l holds Z[l + 32 r]; the conjugate-symmetric partner Z[1024 - k] lives in lane
 //     (32 - l) & 31, so the two real spectra are separated with 32 warp shuffles and no further shared-memory
 //     round trip; the pair (|A_k|^2, |B_k|^2) comes out of one FMUL2 + one FFMA2.
-//   * a CTA is 16 warps (register-limited: one CTA per SM) -> 32 power spectra per iteration, parked in the warps'
-//     transposition tiles with bank-skewed bases.  The Slaney filterbank is then applied with lane = frame: the 16
-//     warps split the filter groups, every weight / bin index is a broadcast, every spectrum read is conflict-free
-//     and the control flow is warp-uniform.
-//   * results leave through a shared staging tile as coalesced rows of 80 mel values in dB.
-//   * the audio of the NEXT iteration is loaded into registers before the filterbank phase, so DRAM latency
-//     hides behind it -- also for the frame pairs that touch the padding / a window edge / the end of the clip
-//     (masked or reflected loads), which the launch order groups into 16-warp iterations of their own: a masked
-//     pair costs its warp ~25 % more instructions, and one such warp per iteration held 15 others at the barrier.
+//   * 16 warps transform 16 pairs per iteration -> 32 power spectra, parked in the warps' transposition tiles with
+//     bank-skewed bases.  The Slaney filterbank is then applied with lane = frame: the 506 weighted bins are split into
+//     16 runs, every weight / bin index is a broadcast, every spectrum read is conflict-free and the control flow is
+//     warp-uniform.  Results leave through a shared staging tile as coalesced rows of 80 mel values in dB.
+//   * two organisations of that iteration (bit-identical results):
+//       logmel_power_ws_kernel   the default bank's batch launches: 16 PRODUCER warps (loads, FFT, spectra) and 8 CONSUMER
+//                                warps (mel phase, store phase) joined by mbarriers, registers split with setmaxnreg
+//       logmel_power_kernel      16 identical warps with one __syncthreads and one mbarrier per iteration and a store phase
+//                                staggered by warp class (generic banks, 512-point flavours, the streaming step's split output)
+//   * frame pairs that touch the padding / a window edge / the end of the clip take masked or reflected loads and are
+//     grouped by the launch order into iterations of their own: a masked pair costs its warp ~25 % more instructions.
 //   * the default bank (sr 16000, 80 mels, 80..8000 Hz) runs the filterbank as straight-line FFMAs with immediate
 //     weights unrolled from compile-time tables (melbank_default.inc); any other bank takes the looped variant.
 #include <algorithm>
@@ -529,8 +531,8 @@ __device__ __forceinline__ void bar_wait_parked(uint32_t bar, uint32_t parity) {
 //   T  transposition through the tile, second FFT, separation -> the pair's two power spectra in the tile
 //   L  the next pair's audio -> registers (in flight during everything below)
 //   B  __syncthreads: all 32 spectra of the iteration are in the tiles
-//   M  mel phase: lane = frame, warp = run of bins -> mel tile [iteration parity]; arrive on the mbarrier
-//   S  store phase of the PREVIOUS iteration's rows (the mel tiles are double buffered), placed per warp class
+//   M  mel phase: lane = frame, warp = run of bins -> mel tiles; arrive on the mbarrier
+//   S  store phase of the PREVIOUS iteration's rows (the tiles hold them until the next B), placed per warp class
 //      (warp / 4, one warp of every class on each scheduler) either before F, between T and L, or after L: the classes
 //      then run the FFT a store phase apart, so that the FMA-bound and the shared-memory-bound stretches of different
 //      warps overlap instead of all 16 warps queueing for the same pipe at the same time.
