@@ -368,6 +368,40 @@ def run_gpu(args):
                        "single-GPU forward of the same clips on rank 0 (bitwise)"
         barrier()
 
+    # ---- the same K steps captured once in a CUDA graph and replayed (no host work between the launches) ----
+    graph_leg = None
+    try:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step(0)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        want = kept.clone()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(K_steps):
+                step(i)
+        graph.replay()
+        barrier()
+        assert torch.equal(kept, want), "graph replay of forward() differs from the eager steps"
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        device_gate()
+        q0.record()
+        graph.replay()
+        q1.record()
+        barrier()
+        tq = torch.tensor([q0.elapsed_time(q1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        graph_leg = {"ms_per_step": float(tq.item()) / K_steps, "unit": UNIT,
+                     "value": world * B * CLIP_SECONDS * K_steps / (float(tq.item()) * 1e-3),
+                     "note": f"the {K_steps} forward() calls of the timed region captured in one CUDA graph and replayed "
+                             "(bitwise the same results; no gather inside); the headline value above is the eager loop"}
+        del graph, want
+    except Exception as e:  # capture is an extra: the contract line does not depend on it
+        graph_leg = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.synchronize()
+
     # ---- roofline leg: the dominant kernel (log-mel power) alone, one event pair per launch ----
     fe = model._frontend(dev)
     n_frames = model.window_frames + 1
@@ -535,6 +569,8 @@ def run_gpu(args):
                                 "(inputs 278.5 MB > L2); bytes = SURVEY section 8(d) per-clip figure x 512",
                          "whole_step_frac_of_hbm": k1_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
         }
+        if graph_leg is not None:
+            line["cuda_graph"] = graph_leg
         if gather_check is not None:
             line["gather_check"] = gather_check
         if other is not None:

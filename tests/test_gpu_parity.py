@@ -504,3 +504,30 @@ def test_folded_weights_follow_in_place_edits_after_invalidate(K):
     assert torch.equal(m(audio, egemaps=eg)["blendshapes"], a)
     with pytest.raises(ValueError):
         m.precision = "tf32"
+
+
+def test_forward_is_cuda_graph_capturable(K):
+    """The whole forward (one native call: six launches chained with programmatic dependent launch, one workspace
+    allocation) can be captured in a CUDA graph and replayed: same bits as the eager call, also after the inputs change."""
+    spec = dict(fps=30, wseed=1235, style="stress", iseed=83, kind="speechlike", B=4, L=136000 + 3 * 533)
+    m, _ = _model(K, spec, True)
+    m.precision = "bf16"
+    audio, eg = _inputs(spec)
+    out = torch.empty(4, m.num_output_frames(audio.shape[1]), 52, device="cuda")
+    want = m(audio, egemaps=eg)["blendshapes"].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        m(audio, egemaps=eg, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        m(audio, egemaps=eg, out=out)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    audio.copy_(torch.roll(audio, 1, 0))            # new clips in the captured buffers
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, m(audio, egemaps=eg)["blendshapes"])
