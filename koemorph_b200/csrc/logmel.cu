@@ -1091,9 +1091,10 @@ extern "C" int koe_debug_k1_variant(int store_order, int warp_specialised) {
 }
 
 extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_args* a, void* stream) {
-  KOE_REQUIRE(fe != nullptr && a != nullptr && a->audio != nullptr && a->power != nullptr,
-              "koe_logmel_power: NULL argument");
+  KOE_REQUIRE(fe != nullptr && a != nullptr, "koe_logmel_power: NULL argument");
   KOE_REQUIRE(a->n_clips >= 0 && a->n_samples >= 0 && a->n_frames >= 0, "koe_logmel_power: negative size");
+  if (a->n_clips == 0 || a->n_frames == 0) return KOE_OK;  // nothing to do: empty buffers may be NULL
+  KOE_REQUIRE(a->audio != nullptr && a->power != nullptr, "koe_logmel_power: NULL buffer");
   KOE_REQUIRE(a->hop > 0 && a->audio_stride >= a->n_samples, "koe_logmel_power: bad hop/stride");
   KOE_REQUIRE(a->frame_offset >= 0 && a->frame_step >= 1 && a->sample_offset >= 0,
               "koe_logmel_power: bad frame_offset/frame_step/sample_offset");

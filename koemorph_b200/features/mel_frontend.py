@@ -110,6 +110,8 @@ class LogMelFrontend:
         if pad_mode not in ("constant", "reflect"):
             raise ValueError(f"pad_mode must be 'constant' or 'reflect', got {pad_mode!r}")
         B, L = audio.shape
+        if L == 0 and B > 0:   # a clip without samples is all padding: nothing is read, but the ABI wants a pointer
+            audio = torch.zeros(B, 1, dtype=torch.float32, device=audio.device)
         if out is None:
             power = torch.empty((B, n_frames, self.n_mels), dtype=torch.float32, device=audio.device)
             fmax = torch.empty((B, n_frames), dtype=torch.float32, device=audio.device)

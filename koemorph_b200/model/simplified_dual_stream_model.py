@@ -232,6 +232,11 @@ class SimplifiedDualStreamModel(nn.Module):
             out = torch.empty(B, n_out, 52, dtype=torch.float32, device=dev)
         elif out.shape != (B, n_out, 52) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
             raise ValueError(f"out must be a contiguous float32 ({B}, {n_out}, 52) tensor on {dev}")
+        if B == 0:   # nothing to launch (and no device pointers to hand over)
+            empty = (lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)) if return_attention else (lambda *shape: None)
+            return out, empty(0, n_out, 52), empty(0, n_out, 28, 80)
+        if L == 0:   # a clip without samples is all padding: the kernels read nothing, but the ABI wants a pointer
+            audio = torch.zeros(B, 1, dtype=torch.float32, device=dev)
         # one workspace allocation per call: mel power (dB) of the global frames and of the edge variants, their per-frame
         # maxima, the emotion stream's per-clip value
         n_main, n_var = B * n_frames, B * n_out

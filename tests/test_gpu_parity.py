@@ -531,3 +531,36 @@ def test_forward_is_cuda_graph_capturable(K):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, m(audio, egemaps=eg)["blendshapes"])
+
+
+@pytest.mark.parametrize("L", [0, 1, 100, 532, 533, 1599, 136447, 136448, 136449])
+def test_tiny_and_boundary_clip_lengths_vs_oracle(K, L):
+    """Ragged edges of the geometry: empty audio, clips shorter than a hop / than three frames (the reference zero-pads the
+    short-term detail, simplified_dual_stream_model.py:206-212), lengths just below / at / above one full window."""
+    spec = dict(fps=30, wseed=1235, style="stress", iseed=90 + L % 7, kind="noise", B=2, L=max(L, 1))
+    m, w = _model(K, spec, True)
+    audio, eg = O.make_inputs(spec["iseed"], 2, max(L, 1), "noise")
+    audio = audio[:, :L]
+    want = O.forward_sequence(w, audio, eg)["blendshapes"]
+    a, e = torch.from_numpy(np.ascontiguousarray(audio)).cuda(), torch.from_numpy(eg).cuda()
+    for prec, tol in (("fp32", OUT_ATOL), ("bf16", BF16_OUT_ATOL)):
+        m.precision = prec
+        got = m(a, egemaps=e)["blendshapes"]
+        assert got.shape == want.shape == (2, 1 if L < 136448 + 533 else 2, 52)
+        _close(got, want, 0, tol, f"L = {L}, {prec}")
+    single = K.SimplifiedDualStreamModel().cuda().eval()
+    single.load_state_dict(O.model_state_dict(w), strict=True)
+    single.set_compression_layer(torch.from_numpy(w["compression.weight"]), torch.from_numpy(w["compression.bias"]))
+    lt, st = single.extract_mel_features(a)
+    ref_lt, ref_st = O.extract_mel_features(audio)
+    _close(lt, ref_lt, LOGMEL_RTOL, LOGMEL_ATOL, f"log-mel, L = {L}")
+    _close(st, ref_st, LOGMEL_RTOL, LOGMEL_ATOL, f"short-term log-mel, L = {L}")
+
+
+def test_empty_batch(K):
+    m, _ = _model(K, dict(fps=30, wseed=1234, style="init"), True)
+    out = m(torch.zeros(0, 136000, device="cuda"), egemaps=torch.zeros(0, 264, device="cuda"))
+    assert out["blendshapes"].shape == (0, 1, 52) and out["num_frames"] == 1
+    from koemorph_b200.infer import HostPipeline
+    host = HostPipeline(m)(torch.zeros(0, 136000).pin_memory(), torch.zeros(0, 264).pin_memory())
+    assert host.shape == (0, 1, 52)
