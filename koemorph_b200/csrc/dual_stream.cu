@@ -614,8 +614,9 @@ static int validate_weights(const koe_core_weights* w) {
 int koe::launch_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid,
                                void* stream, bool after_frontend) {
   if (int rc = validate_weights(w)) return rc;
-  KOE_REQUIRE(emo_in != nullptr && expr_sigmoid != nullptr && n_clips >= 0, "koe_emotion_stream: bad argument");
-  if (n_clips == 0) return KOE_OK;
+  KOE_REQUIRE(n_clips >= 0, "koe_emotion_stream: negative size");
+  if (n_clips == 0) return KOE_OK;  // nothing to do: empty buffers may be NULL
+  KOE_REQUIRE(emo_in != nullptr && expr_sigmoid != nullptr, "koe_emotion_stream: NULL argument");
   static bool configured[64] = {false};
   int dev = 0;
   KOE_CUDA(cudaGetDevice(&dev));
@@ -717,6 +718,7 @@ extern "C" int koe_dual_stream_windows(const koe_core_weights* w, const float* c
                                        const float* expr_sigmoid, float* out, float* sigmoid_out, float* attn_out,
                                        int precision, void* stream) {
   if (int rc = validate_weights(w)) return rc;
+  if (n_clips == 0 || n_out == 0) return KOE_OK;  // nothing to do: empty buffers may be NULL
   KOE_REQUIRE(power != nullptr && frame_max != nullptr && expr_sigmoid != nullptr && out != nullptr,
               "koe_dual_stream_windows: NULL argument");
   KOE_REQUIRE(n_edge >= 0 && n_edge <= KOE_MAX_EDGE, "koe_dual_stream_windows: n_edge out of range");
@@ -800,9 +802,10 @@ extern "C" int koe_dual_stream_features(const koe_core_weights* w, const float* 
                                         const float* mel_short, int n_clips, const float* expr_sigmoid, float* out,
                                         float* sigmoid_out, float* attn_out, int precision, void* stream) {
   if (int rc = validate_weights(w)) return rc;
+  KOE_REQUIRE(n_clips >= 0 && n_long >= 0, "koe_dual_stream_features: bad sizes");
+  if (n_clips == 0) return KOE_OK;  // nothing to do: empty buffers may be NULL
   KOE_REQUIRE(mel_long != nullptr && mel_short != nullptr && expr_sigmoid != nullptr && out != nullptr,
               "koe_dual_stream_features: NULL argument");
-  KOE_REQUIRE(n_clips >= 0 && n_long >= 0, "koe_dual_stream_features: bad sizes");
   KOE_REQUIRE(((reinterpret_cast<uintptr_t>(mel_long) | reinterpret_cast<uintptr_t>(mel_short)) & 15) == 0,
               "koe_dual_stream_features: features must be 16-byte aligned");
   if (n_clips == 0) return KOE_OK;

@@ -564,3 +564,44 @@ def test_empty_batch(K):
     from koemorph_b200.infer import HostPipeline
     host = HostPipeline(m)(torch.zeros(0, 136000).pin_memory(), torch.zeros(0, 264).pin_memory())
     assert host.shape == (0, 1, 52)
+
+
+@pytest.mark.parametrize("fps,W,stride,extra", [(60, 512, 1, 0), (60, 512, 1, 265), (60, 512, 1, 266), (60, 512, 2, 3 * 266 + 1),
+                                                (30, 256, 4, 7 * 533), (30, 256, 7, 20 * 533 + 532)])
+def test_window_count_boundaries_vs_oracle(K, fps, W, stride, extra):
+    """T_out = max(1, (L // hop - W) // stride + 1) at its boundaries, both frame rates, strides that do not divide the
+    surplus (reference sequential_dual_stream_model.py:84-96)."""
+    hop = 16000 // fps
+    L = W * hop + extra
+    spec = dict(fps=fps, wseed=1236, style="stress", iseed=200 + extra % 11, kind="speechlike", B=2, L=L, stride=stride)
+    m, w = _model(K, spec, True)
+    audio, eg = O.make_inputs(spec["iseed"], 2, L, "speechlike")
+    want = O.forward_sequence(w, audio, eg, fps=fps, stride_frames=stride)["blendshapes"]
+    a, e = torch.from_numpy(audio).cuda(), torch.from_numpy(eg).cuda()
+    n_out = max(1, (L // hop - W) // stride + 1)
+    assert want.shape == (2, n_out, 52) and m.num_output_frames(L) == n_out
+    for prec, tol in (("fp32", OUT_ATOL), ("bf16", BF16_OUT_ATOL)):
+        m.precision = prec
+        _close(m(a, egemaps=e)["blendshapes"], want, 0, tol, f"{fps} fps stride {stride} extra {extra} {prec}")
+
+
+def test_core_standalone_degenerate_shapes(K):
+    """DualStreamCrossAttention.forward with one / two long-term frames, far more than the window (truncated, reference
+    dual_stream_attention.py:192-202), and an empty batch."""
+    w = O.make_weights(1235, 30, style="stress")
+    core = K.DualStreamCrossAttention().cuda().eval()
+    core.load_state_dict({k[len("dual_stream_attention."):]: v for k, v in O.model_state_dict(w).items()
+                          if k.startswith("dual_stream_attention.")})
+    rng = np.random.default_rng(6)
+    for T in (1, 2, 700):
+        lt = rng.uniform(0, 1, (3, T, 80)).astype(np.float32)
+        st = rng.uniform(0, 1, (3, 3, 80)).astype(np.float32)
+        emo = rng.standard_normal((3, 256)).astype(np.float32)
+        want = O.dual_stream_core(w, lt, st, emo)["blendshapes"]
+        for prec, tol in (("fp32", OUT_ATOL), ("bf16", BF16_OUT_ATOL)):
+            core.precision = prec
+            got = core(torch.from_numpy(lt).cuda(), torch.from_numpy(st).cuda(), torch.from_numpy(emo).cuda())["blendshapes"]
+            _close(got, want, 0, tol, f"core T = {T} {prec}")
+    core.precision = "fp32"
+    out = core(torch.zeros(0, 5, 80, device="cuda"), torch.zeros(0, 3, 80, device="cuda"), torch.zeros(0, 256, device="cuda"))
+    assert out["blendshapes"].shape == (0, 52)
