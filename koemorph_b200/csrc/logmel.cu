@@ -360,6 +360,19 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Launch chaining of the frontend kernels (programmatic dependent launch, common.cuh).  Both kernels are launched with
+// the programmatic attribute: their CTAs take SMs as the previous kernel of the stream (the core / smoothing kernel of the
+// previous forward, another frontend launch, the streaming step's tail shift) drains, and the prologue above -- tables
+// into shared memory, barrier set-up: it reads nothing but the frontend's own immutable tables -- runs beside that
+// kernel's tail.  Everything after this point reads the audio and writes the mel rows, so it waits for the previous
+// kernel to complete first; only THEN are this kernel's own dependents released (the emotion stream, which reads nothing
+// this kernel writes, takes each SM as this kernel's CTA leaves it): a dependent released before the wait could run
+// while the kernel before this one is still reading the buffers that dependent writes.
+__device__ __forceinline__ void pdl_prologue_done() {
+  pdl_wait();
+  pdl_launch_dependents();
+}
+
 // ---- the per-pair pieces shared by the two kernel organisations below ------------------------------------------------
 // window, first 32-point FFT, twiddles: registers only.  On entry v[bitrev5(n1)] = (a, b)[32 n1 + lane]; on return
 // v[k1] = W_1024^(k1 lane) Y[k1] of column n2 = lane
@@ -550,9 +563,6 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_scratch + kWarps * kScratch);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // the next kernel of the stream (the emotion stream, which reads nothing this kernel writes) may take each SM as soon
-  // as this kernel's CTA leaves it, without the launch gap
-  pdl_launch_dependents();
 
   for (int i = tid; i < kFrameLen; i += kThreads) s_hann[i] = tab.hann[i];
   for (int i = tid; i < 1024; i += kThreads) s_tw[i] = tab.tw[i];
@@ -567,6 +577,7 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_prologue_done();
 
   const unsigned ppc = (unsigned)(p.n_frames + 1) >> 1;  // frame pairs per clip
   const unsigned total_pairs = (unsigned)p.n_clips * ppc;
@@ -670,7 +681,6 @@ logmel_power_ws_kernel(FrontendTables tab, LogmelParams p) {
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pair + 2 * kWarps);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  pdl_launch_dependents();
   for (int i = tid; i < kFrameLen; i += kWsThreads) s_hann[i] = tab.hann[i];
   for (int i = tid; i < 1024; i += kWsThreads) s_tw[i] = tab.tw[i];
   for (int i = tid; i < 4 * kSlots * kTileStride; i += kWsThreads) s_tiles[i] = 0.0f;
@@ -681,6 +691,7 @@ logmel_power_ws_kernel(FrontendTables tab, LogmelParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_prologue_done();
 
   const unsigned ppc = (unsigned)(p.n_frames + 1) >> 1;
   const unsigned total_pairs = (unsigned)p.n_clips * ppc;
@@ -1164,19 +1175,22 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
     p.step_clips = (int)(step / p.mid_pairs);
     p.step_pairs = (int)(step % p.mid_pairs);
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t le;
   if (p.power_b != nullptr) {
     if (fe->default_bank)
-      logmel_power_kernel<true, true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
+      le = launch_after_primary_starts(logmel_power_kernel<true, true>, dim3(grid), dim3(kThreads), kLogmelSmem, st, tab, p);
     else
-      logmel_power_kernel<false, true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
+      le = launch_after_primary_starts(logmel_power_kernel<false, true>, dim3(grid), dim3(kThreads), kLogmelSmem, st, tab, p);
   } else if (fe->default_bank && g_k1_warp_specialised == 1)
-    logmel_power_ws_kernel<8, 96, 48><<<grid, (kWsProducers + 8) * 32, kLogmelWsSmem, (cudaStream_t)stream>>>(tab, p);
+    le = launch_after_primary_starts(logmel_power_ws_kernel<8, 96, 48>, dim3(grid), dim3((kWsProducers + 8) * 32), kLogmelWsSmem,
+                                     st, tab, p);
   else if (fe->default_bank)
-    logmel_power_kernel<true><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
+    le = launch_after_primary_starts(logmel_power_kernel<true>, dim3(grid), dim3(kThreads), kLogmelSmem, st, tab, p);
   else
-    logmel_power_kernel<false><<<grid, kThreads, kLogmelSmem, (cudaStream_t)stream>>>(tab, p);
+    le = launch_after_primary_starts(logmel_power_kernel<false>, dim3(grid), dim3(kThreads), kLogmelSmem, st, tab, p);
   count_launch();
-  KOE_CUDA(cudaGetLastError());
+  KOE_CUDA(le);
   return KOE_OK;
 }
 
