@@ -307,10 +307,13 @@ int koe_stream_push(const koe_stream_args* args, int* emitted, void* stream);
  * The whole forward of SequentialDualStreamModel.forward (src/model/sequential_dual_stream_model.py:63-167) -- or, with
  * n_out = 1 and n_edge = 0, of SimplifiedDualStreamModel.forward (src/model/simplified_dual_stream_model.py:370-415) --
  * as ONE call: koe_logmel_power on the clip's global frames, the 2 * n_edge edge-variant launches on the window grid,
- * koe_emotion_stream, koe_dual_stream_windows and (smooth != 0, n_out > 1) koe_ema_scan, queued back to back on `stream`.
- * Because the call knows which kernel precedes which, the emotion stream and the core are chained to the frontend with
- * programmatic dependent launch (they start on SMs the frontend's last CTAs have left); the public single-kernel entries
- * above keep plain stream order.  Window i of a clip starts at global frame i * stride_frames and holds
+ * the emotion stream, koe_dual_stream_windows and (smooth != 0, n_out > 1) koe_ema_scan, queued back to back on `stream`.
+ * Because the call knows which kernel precedes which, every kernel is chained to the one before it with programmatic
+ * dependent launch (it takes SMs as that kernel's CTAs leave them and orders itself with griddepcontrol.wait); the public
+ * single-kernel entries above keep plain stream order.  The expression entries of `out` depend on the emotion stream only
+ * and the mouth entries on the mel stream only, so here the emotion kernel writes its 24 entries of every output row
+ * itself (and expr_sigmoid, as koe_emotion_stream would) and the core leaves them alone: neither waits for the other's
+ * results.  Window i of a clip starts at global frame i * stride_frames and holds
  * frames_per_window frames; n_frames >= (n_out - 1) * stride_frames + frames_per_window global frames are computed.
  * Workspace (caller-owned): power[0] / frame_max[0] [n_clips][n_frames][80] / [n_clips][n_frames]; for m < n_edge
  * power[1 + 2m], power[2 + 2m] [n_clips][n_out][80] (+ frame_max); expr_sigmoid [n_clips].

@@ -36,8 +36,13 @@ __device__ __forceinline__ long long window_row(const CoreParams& p, int variant
                       : (long long)b * p.n_out + wi;
 }
 
-// emotion stream launch shared by the public entry and the fused forward (csrc/session.cu); see dual_stream.cu
-int launch_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid, void* stream,
-                          bool after_frontend);
+// emotion stream launch shared by the public entry and the fused forward (csrc/session.cu, which has it write the
+// expression entries of `out`); the core launch that leaves those entries alone (expr_sigmoid == NULL); see dual_stream.cu
+int launch_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid, float* out,
+                          float* sigmoid_out, int n_out, void* stream, bool after_frontend);
+int launch_dual_stream_windows(const koe_core_weights* w, const float* const* power, const float* const* frame_max, int n_edge,
+                               int n_clips, int n_frames, int n_out, int stride_frames, int frames_per_window,
+                               const float* expr_sigmoid, float* out, float* sigmoid_out, float* attn_out, int precision,
+                               void* stream, bool expr_by_emotion_kernel);
 
 }  // namespace koe

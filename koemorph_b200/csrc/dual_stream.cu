@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kCoreThreads, 1) dual_stream_fp32_kernel(CoreP
         }
       }
     }
-    if (tid < KOE_N_EXPR) {
+    if (tid < KOE_N_EXPR && p.expr_sigmoid != nullptr) {  // (NULL: the fused forward's emotion kernel writes these)
       const float y = __ldg(p.expr_sigmoid + b);
       const int idx = __ldg(W.expr_idx + tid);
       const size_t o_off = (size_t)item * KOE_N_BLENDSHAPES + idx;
@@ -336,185 +336,256 @@ __global__ void __launch_bounds__(kCoreThreads, 1) dual_stream_fp32_kernel(CoreP
   }
 }
 
-// ---- emotion stream: NC clips per CTA (16 for large batches, 4 when that leaves most SMs idle), weights streamed
-// through shared memory in 64-row cp.async chunks
-constexpr int kEmoClipsMax = 16;
 constexpr int kEmoInMax = 272;
-constexpr int kEmoChunkRows = 64;
-constexpr int kEmoBufFloats = kEmoChunkRows * kD;   // one chunk buffer: 64 rows of up to 256 floats (64 KB)
-constexpr size_t kEmoSmem = sizeof(float) * (2 * kEmoBufFloats + kEmoInMax * kEmoClipsMax + kD * kEmoClipsMax + 16 * 8 + 32);
 
-template <int kEmoClips>
-__global__ void __launch_bounds__(256) emotion_stream_kernel(koe_core_weights W, const float* __restrict__ emo_in,
-                                                             int n_clips, float* __restrict__ expr_sigmoid) {
-  extern __shared__ __align__(16) float esm[];
-  float* s_buf = esm;                                   // [2][64][<=256]
-  float* s_x = s_buf + 2 * kEmoBufFloats;               // [emo_in][16]  (clip-contiguous: broadcast float4 loads)
-  float* s_z = s_x + kEmoInMax * kEmoClips;             // [256][16]
-  float* s_red = s_z + kD * kEmoClips;                  // [16][8]
-  float* s_stat = s_red + 16 * 8;                       // [16][2]
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  pdl_launch_dependents();  // the core kernel may set itself up (barriers, TMEM, constants) while this one runs
-  const int c0 = blockIdx.x * kEmoClips;
-  const int nc = min(kEmoClips, n_clips - c0);
-  const int n1 = (W.emo_in + kEmoChunkRows - 1) / kEmoChunkRows;   // chunks of we1_t [emo_in][256]
-  const int n2 = kD / kEmoChunkRows;                               // chunks of we2_t [256][128]
+// ---- emotion stream (reference dual_stream_attention.py:234-240 with the 264 -> 256 compression folded in): two GEMVs
+// around a LayerNorm per clip, x [emo_in] -> z [256] -> LayerNorm -> relu(h [128]) . w2 -> sigmoid.
+// The expression blendshapes depend on the emotion stream ONLY and the mouth blendshapes on the mel stream only, so in the
+// fused forward (csrc/session.cu) this kernel writes its 24 entries of every output row itself and the core skips them:
+// the core does not wait for this kernel's results, and this kernel -- a few dozen CTAs, ~9 us each -- runs on the SMs
+// that the frontend's CTAs leave first (their ends are spread over ~15 us), done about when the last of them is.
+//   * weights arrive through a ring of 32 KiB stages, one cp.async.bulk (TMA) each, issued by a producer warp: 32 rows of
+//     we1_t [emo_in][256], then 64 rows of we2_t [256][128]
+//   * register tiles: a thread owns 4 output features x NC clips (NC / 2 packed FFMA2 per feature and weight row: one
+//     16-byte weight load, NC / 4 broadcast 16-byte input loads); a warp is one K slice (rows k = slice mod 4 / 8) of 128
+//     features, the slices' partial sums meet in shared memory in a fixed order
+//   * everything else the CTA reads (inputs, biases, LayerNorm vectors, output constants) is requested at once at the
+//     start: eight warps cannot hide one memory latency per phase
+constexpr int kEt2Stage = 32768;
+constexpr int kEt2Rows1 = kEt2Stage / (kD * 4);      // 32 rows of we1_t per stage
+constexpr int kEt2Rows2 = kEt2Stage / (128 * 4);     // 64 rows of we2_t per stage
+constexpr int kEt2Threads = 288;                     // 8 consumer warps + the producer warp
+constexpr int kEt2XLoads = (kEmoInMax + 255) / 256;  // input values per thread per clip
+template <int NC>
+struct Et2 {
+  static constexpr int kSlots = NC > 8 ? 3 : 4;
+  static constexpr size_t kSmem = (size_t)kSlots * kEt2Stage + sizeof(float) * (kEmoInMax * NC   // x [k][clip]
+                                                                               + 4 * NC * kD      // partial sums
+                                                                               + kD * NC          // LayerNorm output [k][clip]
+                                                                               + 5 * kD)          // be1, eln_g, eln_b, be2, w2
+                                  + 8 * 2 * kSlots + 16;
+};
 
-  auto issue = [&](int c) {  // chunk c of the concatenated chunk sequence -> buffer c & 1
-    const float* src;
-    int floats;
-    if (c < n1) {
-      const int r0 = c * kEmoChunkRows;
-      src = W.we1_t + (size_t)r0 * kD;
-      floats = min(kEmoChunkRows, W.emo_in - r0) * kD;
-    } else {
-      src = W.we2_t + (size_t)(c - n1) * kEmoChunkRows * 128;
-      floats = kEmoChunkRows * 128;
-    }
-    float* dst = s_buf + (c & 1) * kEmoBufFloats;
-    for (int i = tid; i < floats / 4; i += 256) cp_async16(dst + 4 * i, src + 4 * i);
-    cp_async_commit();
-  };
-  issue(0);
-  issue(1);
-  for (int i = tid; i < kEmoClips * W.emo_in; i += 256) {
-    const int c = i / W.emo_in, k = i % W.emo_in;
-    s_x[k * kEmoClips + c] = c < nc ? emo_in[(size_t)(c0 + c) * W.emo_in + k] : 0.0f;
+template <int NP>  // NP = clips / 2: one packed accumulator per feature and clip pair
+__device__ __forceinline__ void et2_row(const float4 w, const float4* __restrict__ x, float2 (&acc)[4][NP]) {
+  const float wf[4] = {w.x, w.y, w.z, w.w};
+  float2 x2[NP];
+#pragma unroll
+  for (int q = 0; q < NP / 2; ++q) {
+    const float4 v = x[q];
+    x2[2 * q] = make_float2(v.x, v.y), x2[2 * q + 1] = make_float2(v.z, v.w);
   }
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+#pragma unroll
+    for (int c = 0; c < NP; ++c) acc[f][c] = __ffma2_rn(make_float2(wf[f], wf[f]), x2[c], acc[f][c]);
+}
 
-  // ---- z[c][n] = we1_t[:, n] . x[c] + be1[n]   (thread = feature n, 16 clips in registers)
-  float z[kEmoClips];
-  {
-    const float b = __ldg(W.be1 + tid);
-#pragma unroll
-    for (int c = 0; c < kEmoClips; ++c) z[c] = b;
-  }
-  int chunk = 0;
-  for (; chunk < n1; ++chunk) {
-    cp_async_wait<1>();
-    __syncthreads();
-    const float* wb = s_buf + (chunk & 1) * kEmoBufFloats + tid;
-    const int r0 = chunk * kEmoChunkRows, rows = min(kEmoChunkRows, W.emo_in - r0);
-    // eight rows per step: the 8 weight loads and 8 broadcast input loads are issued together (two warps per scheduler
-    // cannot hide a shared-memory round trip per row: `short_scoreboard` was 37 % of the samples)
-    const float4* xr0 = reinterpret_cast<const float4*>(s_x + r0 * kEmoClips);
-    int k = 0;
-    for (; k + 8 <= rows; k += 8) {
-      float w[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) w[u] = wb[(k + u) * kD];
-#pragma unroll
-      for (int q = 0; q < kEmoClips / 4; ++q) {
-        float4 x[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = xr0[(k + u) * (kEmoClips / 4) + q];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          z[4 * q + 0] = fmaf(w[u], x[u].x, z[4 * q + 0]);
-          z[4 * q + 1] = fmaf(w[u], x[u].y, z[4 * q + 1]);
-          z[4 * q + 2] = fmaf(w[u], x[u].z, z[4 * q + 2]);
-          z[4 * q + 3] = fmaf(w[u], x[u].w, z[4 * q + 3]);
-        }
-      }
+__device__ __forceinline__ long long global_ns() {
+  unsigned long long g;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+  return (long long)g;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kEt2Threads, 1)
+emotion_tiled_kernel(koe_core_weights W, const float* __restrict__ emo_in, int n_clips, float* __restrict__ expr_sigmoid,
+                     float* __restrict__ out, float* __restrict__ sigmoid_out, int n_out, long long* dbg) {
+  constexpr int kSlots = Et2<NC>::kSlots, NP = NC / 2;
+  extern __shared__ __align__(128) unsigned char et2_smem[];
+  unsigned char* s_ring = et2_smem;
+  float* s_x = reinterpret_cast<float*>(et2_smem + kSlots * kEt2Stage);     // [emo_in_pad][NC]
+  float* s_part = s_x + kEmoInMax * NC;                                      // [slice][clip][feature]
+  float* s_zn = s_part + 4 * NC * kD;                                        // [256][NC]
+  float* s_vec = s_zn + kD * NC;                                             // be1 | eln_g | eln_b | be2 (128) . w2 (128)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_vec + 5 * kD);
+  const uint32_t bar_full = smem_u32addr(s_bar), bar_empty = bar_full + 8 * kSlots;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = blockIdx.x * NC;
+  const int nc = min(NC, n_clips - c0);
+  const int n1 = (W.emo_in_pad + kEt2Rows1 - 1) / kEt2Rows1, n2 = kD / kEt2Rows2;
+  if (dbg != nullptr && tid == 0) dbg[3 * blockIdx.x] = global_ns();  // (scripts/chain_timeline.py)
+  if (tid == 0) {
+    for (int i = 0; i < kSlots; ++i) {
+      mbarrier_init(bar_full + 8 * i, 1);
+      mbarrier_init(bar_empty + 8 * i, 8);
     }
-    for (; k < rows; ++k) {
-      const float w = wb[k * kD];
-#pragma unroll
-      for (int q = 0; q < kEmoClips / 4; ++q) {
-        const float4 x = xr0[k * (kEmoClips / 4) + q];
-        z[4 * q + 0] = fmaf(w, x.x, z[4 * q + 0]);
-        z[4 * q + 1] = fmaf(w, x.y, z[4 * q + 1]);
-        z[4 * q + 2] = fmaf(w, x.z, z[4 * q + 2]);
-        z[4 * q + 3] = fmaf(w, x.w, z[4 * q + 3]);
-      }
-    }
-    __syncthreads();
-    if (chunk + 2 < n1 + n2) issue(chunk + 2); else cp_async_commit();
-  }
-  // ---- LayerNorm per clip over the 256 threads (two passes)
-#pragma unroll
-  for (int c = 0; c < kEmoClips; ++c) {
-    const float v = warp_sum(z[c]);
-    if (tx == 0) s_red[c * 8 + ty] = v;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid < kEmoClips) {
-    float v = 0.0f;
-    for (int w = 0; w < 8; ++w) v += s_red[tid * 8 + w];
-    s_stat[tid * 2] = v * (1.0f / kD);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int c = 0; c < kEmoClips; ++c) {
-    const float d = z[c] - s_stat[c * 2];
-    const float v = warp_sum(d * d);
-    if (tx == 0) s_red[c * 8 + ty] = v;
-  }
-  __syncthreads();
-  if (tid < kEmoClips) {
-    float v = 0.0f;
-    for (int w = 0; w < 8; ++w) v += s_red[tid * 8 + w];
-    s_stat[tid * 2 + 1] = rsqrtf(v * (1.0f / kD) + W.ln_eps);
-  }
-  __syncthreads();
-  {
-    const float g = __ldg(W.eln_g + tid), be = __ldg(W.eln_b + tid);
-#pragma unroll
-    for (int c = 0; c < kEmoClips; ++c)
-      s_z[tid * kEmoClips + c] = (z[c] - s_stat[c * 2]) * s_stat[c * 2 + 1] * g + be;
-  }
-  // ---- h[c][j] = relu(we2_t[:, j] . zn[c] + be2[j]); thread = (j = tid & 127, clip half = tid >> 7)
-  const int j = tid & 127, half = tid >> 7;
-  float h[kEmoClips / 2];
-  {
-    const float b = __ldg(W.be2 + j);
-#pragma unroll
-    for (int c = 0; c < kEmoClips / 2; ++c) h[c] = b;
-  }
-  for (; chunk < n1 + n2; ++chunk) {
-    cp_async_wait<1>();
-    __syncthreads();   // also orders the s_z writes above before the first read
-    const float* wb = s_buf + (chunk & 1) * kEmoBufFloats + j;
-    const int r0 = (chunk - n1) * kEmoChunkRows;
-#pragma unroll 8
-    for (int k = 0; k < kEmoChunkRows; ++k) {
-      const float w = wb[k * 128];
-      const float* zr = s_z + (r0 + k) * kEmoClips + half * (kEmoClips / 2);
-      if constexpr (kEmoClips / 2 >= 4) {
-#pragma unroll
-        for (int q = 0; q < kEmoClips / 8; ++q) {
-          const float4 x = reinterpret_cast<const float4*>(zr)[q];
-          h[4 * q + 0] = fmaf(w, x.x, h[4 * q + 0]);
-          h[4 * q + 1] = fmaf(w, x.y, h[4 * q + 1]);
-          h[4 * q + 2] = fmaf(w, x.z, h[4 * q + 2]);
-          h[4 * q + 3] = fmaf(w, x.w, h[4 * q + 3]);
-        }
+  // Launched behind the frontend with the programmatic attribute: this kernel reads nothing the frontend writes (the
+  // frontend released it after its own wait, so everything queued before THAT has completed).  The next kernel of the
+  // stream (the core) may set itself up beside this one; it orders itself by its own griddepcontrol.wait.
+  pdl_launch_dependents();
+
+  if (warp == 8) {
+    // ===================================================== weight producer =============================
+    // The whole warp runs the loop and one lane issues: lanes that left it early would sit in the griddepcontrol.wait at
+    // the end of the kernel, and that stalls the WARP -- the issuing lane with it -- until the previous kernel has
+    // completed (measured: the weight stages arrived 11 us late, exactly when that kernel ended).
+    uint32_t slot = 0, phase = 0;
+    for (int c = 0; c < n1 + n2; ++c) {
+      mbarrier_wait(bar_empty + 8 * slot, phase ^ 1);
+      const float* src;
+      uint32_t bytes;
+      if (c < n1) {
+        src = W.we1_t + (size_t)c * kEt2Rows1 * kD;
+        bytes = (uint32_t)min(kEt2Rows1, W.emo_in_pad - c * kEt2Rows1) * kD * 4;
       } else {
-        static_assert(kEmoClips / 2 == 2, "clips per half: 2 or a multiple of 4");
-        const float2 x = *reinterpret_cast<const float2*>(zr);
-        h[0] = fmaf(w, x.x, h[0]);
-        h[1] = fmaf(w, x.y, h[1]);
+        src = W.we2_t + (size_t)(c - n1) * kEt2Rows2 * 128;
+        bytes = kEt2Stage;
+      }
+      if (lane == 0) {
+        mbarrier_expect_tx(bar_full + 8 * slot, bytes);
+        bulk_copy_g2s(smem_u32addr(s_ring + slot * kEt2Stage), src, bytes, bar_full + 8 * slot);
+      }
+      __syncwarp();
+      if (++slot == kSlots) slot = 0, phase ^= 1;
+    }
+  } else {
+    // ===================================================== consumers ===================================
+    // inputs, clip-contiguous (x[k][0..NC): broadcast 16-byte loads per weight row; rows beyond emo_in read as zero)
+    {
+      float xv[NC][kEt2XLoads];
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int j = 0; j < kEt2XLoads; ++j) {
+          const int k = tid + 256 * j;
+          xv[c][j] = (c < nc && k < W.emo_in) ? __ldg(emo_in + (size_t)(c0 + c) * W.emo_in + k) : 0.0f;
+        }
+      const float v0 = __ldg(W.be1 + tid), v1 = __ldg(W.eln_g + tid), v2 = __ldg(W.eln_b + tid);
+      const float v3 = tid < 128 ? __ldg(W.be2 + tid) : __ldg(W.w2 + tid - 128);
+#pragma unroll
+      for (int j = 0; j < kEt2XLoads; ++j) {
+        const int k = tid + 256 * j;
+        if (k < W.emo_in_pad) {
+#pragma unroll
+          for (int q = 0; q < NC / 4; ++q)
+            *reinterpret_cast<float4*>(s_x + k * NC + 4 * q) =
+                make_float4(xv[4 * q][j], xv[4 * q + 1][j], xv[4 * q + 2][j], xv[4 * q + 3][j]);
+        }
+      }
+      s_vec[tid] = v0, s_vec[kD + tid] = v1, s_vec[2 * kD + tid] = v2, s_vec[3 * kD + tid] = v3;
+    }
+    int o_idx = 0;
+    float o_coef = 0.0f;
+    if (lane < KOE_N_EXPR) {
+      o_idx = __ldg(W.expr_idx + lane);
+      o_coef = __ldg(W.coef + o_idx);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float *s_be1 = s_vec, *s_g = s_vec + kD, *s_b = s_vec + 2 * kD, *s_be2 = s_vec + 3 * kD, *s_w2 = s_vec + 3 * kD + 128;
+    uint32_t slot = 0, phase = 0;
+    float2 acc[4][NP];
+    // ---- layer 1: z = we1_t^T x.  warp = (K slice = warp >> 1, feature block = warp & 1); thread: features 4 fl .. 4 fl + 3
+    {
+      const int slice = warp >> 1, fl = 32 * (warp & 1) + lane;
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int c = 0; c < NP; ++c) acc[f][c] = make_float2(0.0f, 0.0f);
+      for (int ch = 0; ch < n1; ++ch) {
+        mbarrier_wait(bar_full + 8 * slot, phase);
+        const float4* wrow = reinterpret_cast<const float4*>(s_ring + slot * kEt2Stage) + fl;
+        const int r0 = ch * kEt2Rows1, rows = min(kEt2Rows1, W.emo_in_pad - r0);
+#pragma unroll
+        for (int j = 0; j < kEt2Rows1 / 4; ++j) {
+          const int r = slice + 4 * j;
+          if (r < rows) et2_row<NP>(wrow[r * (kD / 4)], reinterpret_cast<const float4*>(s_x + (r0 + r) * NC), acc);
+        }
+        __syncwarp();
+        if (lane == 0) mbarrier_arrive(bar_empty + 8 * slot);
+        if (++slot == kSlots) slot = 0, phase ^= 1;
+      }
+      float* dst = s_part + (size_t)slice * NC * kD + 4 * fl;
+#pragma unroll
+      for (int c = 0; c < NP; ++c) {
+        *reinterpret_cast<float4*>(dst + (2 * c) * kD) = make_float4(acc[0][c].x, acc[1][c].x, acc[2][c].x, acc[3][c].x);
+        *reinterpret_cast<float4*>(dst + (2 * c + 1) * kD) = make_float4(acc[0][c].y, acc[1][c].y, acc[2][c].y, acc[3][c].y);
       }
     }
-    __syncthreads();
-    if (chunk + 2 < n1 + n2) issue(chunk + 2); else cp_async_commit();
-  }
-  {
-    const float w2 = __ldg(W.w2 + j);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- bias, LayerNorm (two passes): a warp takes clips warp, warp + 8; lane: features lane + 32 j
+    for (int c = warp; c < NC; c += 8) {
+      float z[8];
+      float sum = 0.0f;
 #pragma unroll
-    for (int c = 0; c < kEmoClips / 2; ++c) {
-      const float v = warp_sum(fmaxf(h[c], 0.0f) * w2);
-      if (tx == 0) s_red[(half * (kEmoClips / 2) + c) * 8 + (ty & 3)] = v;
+      for (int j = 0; j < 8; ++j) {
+        const int f = lane + 32 * j;
+        float v = s_be1[f];
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) v += s_part[((size_t)sl * NC + c) * kD + f];
+        z[j] = v;
+        sum += v;
+      }
+      const float mean = warp_sum(sum) * (1.0f / kD);
+      float sq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sq = fmaf(z[j] - mean, z[j] - mean, sq);
+      const float rstd = rsqrtf(warp_sum(sq) * (1.0f / kD) + W.ln_eps);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int f = lane + 32 * j;
+        s_zn[f * NC + c] = (z[j] - mean) * rstd * s_g[f] + s_b[f];
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- layer 2: h = we2_t^T zn.  warp = K slice (rows k = warp mod 8); thread: hidden features 4 lane .. 4 lane + 3
+    {
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int c = 0; c < NP; ++c) acc[f][c] = make_float2(0.0f, 0.0f);
+      for (int ch = 0; ch < n2; ++ch) {
+        mbarrier_wait(bar_full + 8 * slot, phase);
+        const float4* wrow = reinterpret_cast<const float4*>(s_ring + slot * kEt2Stage) + lane;
+#pragma unroll
+        for (int j = 0; j < kEt2Rows2 / 8; ++j) {
+          const int r = warp + 8 * j;
+          et2_row<NP>(wrow[r * (128 / 4)], reinterpret_cast<const float4*>(s_zn + (ch * kEt2Rows2 + r) * NC), acc);
+        }
+        __syncwarp();
+        if (lane == 0) mbarrier_arrive(bar_empty + 8 * slot);
+        if (++slot == kSlots) slot = 0, phase ^= 1;
+      }
+      float* dst = s_part + (size_t)warp * NC * 128 + 4 * lane;   // [slice 8][clip][128]
+#pragma unroll
+      for (int c = 0; c < NP; ++c) {
+        *reinterpret_cast<float4*>(dst + (2 * c) * 128) = make_float4(acc[0][c].x, acc[1][c].x, acc[2][c].x, acc[3][c].x);
+        *reinterpret_cast<float4*>(dst + (2 * c + 1) * 128) = make_float4(acc[0][c].y, acc[1][c].y, acc[2][c].y, acc[3][c].y);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- relu, output layer, sigmoid; the clip's expression entries of every output row
+    for (int c = warp; c < nc; c += 8) {
+      float part = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = lane + 32 * q;
+        float h = s_be2[j];
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) h += s_part[((size_t)sl * NC + c) * 128 + j];
+        part = fmaf(fmaxf(h, 0.0f), s_w2[j], part);
+      }
+      const float logit = warp_sum(part) + W.b2;
+      const float y = 1.0f / (1.0f + expf(-logit));
+      if (lane == 0 && expr_sigmoid != nullptr) expr_sigmoid[c0 + c] = y;
+      if (out != nullptr && lane < KOE_N_EXPR) {
+        const float v = fminf(fmaxf(o_coef * y, 0.0f), 1.0f);
+        size_t o = (size_t)(c0 + c) * n_out * KOE_N_BLENDSHAPES + o_idx;
+        for (int wi = 0; wi < n_out; ++wi, o += KOE_N_BLENDSHAPES) {
+          out[o] = v;
+          if (sigmoid_out != nullptr) sigmoid_out[o] = y;
+        }
+      }
     }
   }
-  __syncthreads();
-  if (tid < nc) {
-    const float logit = s_red[tid * 8] + s_red[tid * 8 + 1] + s_red[tid * 8 + 2] + s_red[tid * 8 + 3] + W.b2;
-    expr_sigmoid[c0 + tid] = 1.0f / (1.0f + expf(-logit));
-  }
-  // this kernel reads nothing the frontend writes, so it may run beside the frontend's last CTAs; it still must not
-  // complete before the frontend has: the core kernel waits on THIS kernel only
+  // the kernel before this one (the frontend) must have completed before this one does: the core, queued next, waits on
+  // THIS kernel only
+  if (dbg != nullptr && tid == 0) dbg[3 * blockIdx.x + 1] = global_ns();
   pdl_wait();
+  if (dbg != nullptr && tid == 0) dbg[3 * blockIdx.x + 2] = global_ns();
 }
 
 // ---- EMA scan: y_t = alpha x_t + (1 - alpha) y_{t-1}, warp-parallel over 32 frames per step --------
@@ -608,47 +679,53 @@ static int validate_weights(const koe_core_weights* w) {
   return KOE_OK;
 }
 
-// `after_frontend`: the caller guarantees that the kernel queued just before this one on `stream` is the log-mel frontend,
-// which writes nothing this kernel reads -- only then may it start beside that kernel's last CTAs (programmatic dependent
-// launch).  From the public entry the producer of emo_in may be the previous kernel, so that launch keeps full stream order.
-int koe::launch_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid,
-                               void* stream, bool after_frontend) {
+static long long* g_tc_debug = nullptr;  // (koe_debug_set_tc_timestamps below)
+
+// One launcher for the public entry (expr_sigmoid only, plain stream order: the producer of emo_in may be the kernel
+// queued just before) and the fused forward (`after_frontend`: the caller guarantees that the kernel queued just before
+// this one is the log-mel frontend, which writes nothing this kernel reads -- only then may it start beside that kernel's
+// last CTAs; `out` != NULL: the expression entries of the n_out output rows of every clip are written here).
+int koe::launch_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid, float* out,
+                               float* sigmoid_out, int n_out, void* stream, bool after_frontend) {
   if (int rc = validate_weights(w)) return rc;
-  KOE_REQUIRE(n_clips >= 0, "koe_emotion_stream: negative size");
+  KOE_REQUIRE(n_clips >= 0 && n_out >= 1, "koe_emotion_stream: bad size");
   if (n_clips == 0) return KOE_OK;  // nothing to do: empty buffers may be NULL
-  KOE_REQUIRE(emo_in != nullptr && expr_sigmoid != nullptr, "koe_emotion_stream: NULL argument");
+  KOE_REQUIRE(emo_in != nullptr && (expr_sigmoid != nullptr || out != nullptr), "koe_emotion_stream: NULL argument");
+  KOE_REQUIRE(w->emo_in_pad % 8 == 0 && w->emo_in_pad <= kEmoInMax, "koe_emotion_stream: emo_in_pad must be a multiple of 8");
+  KOE_REQUIRE(((reinterpret_cast<uintptr_t>(w->we1_t) | reinterpret_cast<uintptr_t>(w->we2_t)) & 15) == 0,
+              "koe_emotion_stream: weights must be 16-byte aligned");
   static bool configured[64] = {false};
   int dev = 0;
   KOE_CUDA(cudaGetDevice(&dev));
   KOE_REQUIRE(dev >= 0 && dev < 64, "device index too large");
   if (!configured[dev]) {
-    KOE_CUDA(cudaFuncSetAttribute(emotion_stream_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmoSmem));
-    KOE_CUDA(cudaFuncSetAttribute(emotion_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEmoSmem));
+    KOE_CUDA(cudaFuncSetAttribute(emotion_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Et2<8>::kSmem));
+    KOE_CUDA(cudaFuncSetAttribute(emotion_tiled_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Et2<16>::kSmem));
     configured[dev] = true;
   }
-  // every CTA streams all the weights (0.4 MB, L2 resident): few clips per CTA while that keeps the grid within ~4 waves
-  const bool small = n_clips <= 4 * 600;
-  const dim3 grid(small ? (n_clips + 3) / 4 : (n_clips + 15) / 16);
+  // every CTA streams all the weights (0.4 MB).  Eight clips per CTA: 64 CTAs of ~9 us for 512 clips, which start on the
+  // SMs the frontend's earliest CTAs leave and are done about when its last CTA is (step 207.9 -> 198.9 us against the
+  // round-1 kernel, 4 clips per CTA and cp.async staging; sixteen clips per CTA, 32 CTAs of ~15 us: 204.6 us).  Sixteen only
+  // where the weight traffic of eight would show (thousands of CTAs).
+  const bool wide = n_clips > 2048;
+  const dim3 grid(wide ? (n_clips + 15) / 16 : (n_clips + 7) / 8), block(kEt2Threads);
+  const size_t smem = wide ? Et2<16>::kSmem : Et2<8>::kSmem;
+  auto kernel = wide ? emotion_tiled_kernel<16> : emotion_tiled_kernel<8>;
+  long long* dbg = after_frontend && g_tc_debug != nullptr ? g_tc_debug + 128 + 2 * 148 : nullptr;
   if (after_frontend) {
-    if (small)
-      KOE_CUDA(launch_after_primary_starts(emotion_stream_kernel<4>, grid, dim3(256), kEmoSmem, (cudaStream_t)stream, *w,
-                                           emo_in, n_clips, expr_sigmoid));
-    else
-      KOE_CUDA(launch_after_primary_starts(emotion_stream_kernel<16>, grid, dim3(256), kEmoSmem, (cudaStream_t)stream, *w,
-                                           emo_in, n_clips, expr_sigmoid));
-  } else if (small) {
-    emotion_stream_kernel<4><<<grid, 256, kEmoSmem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
+    KOE_CUDA(launch_after_primary_starts(kernel, grid, block, smem, (cudaStream_t)stream, *w, emo_in, n_clips, expr_sigmoid, out,
+                                         sigmoid_out, n_out, dbg));
   } else {
-    emotion_stream_kernel<16><<<grid, 256, kEmoSmem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid);
+    kernel<<<grid, block, smem, (cudaStream_t)stream>>>(*w, emo_in, n_clips, expr_sigmoid, out, sigmoid_out, n_out, dbg);
+    KOE_CUDA(cudaGetLastError());
   }
   count_launch();
-  KOE_CUDA(cudaGetLastError());
   return KOE_OK;
 }
 
 extern "C" int koe_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_clips, float* expr_sigmoid,
                                   void* stream) {
-  return koe::launch_emotion_stream(w, emo_in, n_clips, expr_sigmoid, stream, /*after_frontend=*/false);
+  return koe::launch_emotion_stream(w, emo_in, n_clips, expr_sigmoid, nullptr, nullptr, 1, stream, /*after_frontend=*/false);
 }
 
 // ---- y = x W^T + b for a handful of rows: the 264 -> 256 eGeMAPS compression as a stand-alone call
@@ -681,7 +758,6 @@ extern "C" int koe_affine_rows(const float* x, int n_rows, int n_in, const float
   return KOE_OK;
 }
 
-static long long* g_tc_debug = nullptr;
 // bring-up / profiling hook (not in the public header; scripts/tc_timeline.py): a device buffer of 128 + 2 * gridDim
 // 64-bit slots that the tensor-core kernel fills with phase timestamps of CTA 0 (clock64) and every CTA's start / end
 // (globaltimer); NULL (the default) turns the stamps off
@@ -717,10 +793,20 @@ extern "C" int koe_dual_stream_windows(const koe_core_weights* w, const float* c
                                        int n_out, int stride_frames, int frames_per_window,
                                        const float* expr_sigmoid, float* out, float* sigmoid_out, float* attn_out,
                                        int precision, void* stream) {
+  return koe::launch_dual_stream_windows(w, power, frame_max, n_edge, n_clips, n_frames, n_out, stride_frames,
+                                         frames_per_window, expr_sigmoid, out, sigmoid_out, attn_out, precision, stream,
+                                         /*expr_by_emotion_kernel=*/false);
+}
+
+int koe::launch_dual_stream_windows(const koe_core_weights* w, const float* const* power, const float* const* frame_max,
+                                    int n_edge, int n_clips, int n_frames, int n_out, int stride_frames,
+                                    int frames_per_window, const float* expr_sigmoid, float* out, float* sigmoid_out,
+                                    float* attn_out, int precision, void* stream, bool expr_by_emotion_kernel) {
   if (int rc = validate_weights(w)) return rc;
   if (n_clips == 0 || n_out == 0) return KOE_OK;  // nothing to do: empty buffers may be NULL
-  KOE_REQUIRE(power != nullptr && frame_max != nullptr && expr_sigmoid != nullptr && out != nullptr,
-              "koe_dual_stream_windows: NULL argument");
+  KOE_REQUIRE(power != nullptr && frame_max != nullptr && out != nullptr, "koe_dual_stream_windows: NULL argument");
+  // the expression entries of `out` come from expr_sigmoid -- or, in the fused forward, from the emotion kernel itself
+  KOE_REQUIRE((expr_sigmoid != nullptr) != expr_by_emotion_kernel, "koe_dual_stream_windows: NULL expr_sigmoid");
   KOE_REQUIRE(n_edge >= 0 && n_edge <= KOE_MAX_EDGE, "koe_dual_stream_windows: n_edge out of range");
   KOE_REQUIRE(n_clips >= 0 && n_out >= 0 && stride_frames >= 1 && frames_per_window >= 1,
               "koe_dual_stream_windows: bad sizes");

@@ -279,6 +279,8 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   // everything above touched only this CTA's shared memory, TMEM and the weights; the mel rows, frame maxima and
   // emotion-stream outputs read below come from the previous kernels of the stream
   pdl_wait();
+  // (no griddepcontrol.launch_dependents here: released early, the next forward's frontend CTAs take the SMs that this
+  // kernel's last partial round of windows leaves idle and the step gets 11 us SLOWER -- measured, 198.6 vs 209.5 us)
 
   const int n_items = p.n_clips * p.n_out;
   const int T = p.frames_per_window;
@@ -819,7 +821,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
           p.out[o_off] = fminf(fmaxf(__ldg(W.coef + idx) * y, 0.0f), 1.0f);
           if (p.sigmoid_out != nullptr) p.sigmoid_out[o_off] = y;
         }
-      } else if (warp == 1 && lane < KOE_N_EXPR) {
+      } else if (warp == 1 && lane < KOE_N_EXPR && p.expr_sigmoid != nullptr) {  // (NULL: the emotion kernel writes these)
         const float y = __ldg(p.expr_sigmoid + b);
         const int idx = __ldg(W.expr_idx + lane);
         const size_t o_off = (size_t)item * KOE_N_BLENDSHAPES + idx;

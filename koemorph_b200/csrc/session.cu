@@ -158,12 +158,16 @@ extern "C" int koe_forward_windows(const koe_forward_args* a, void* stream) {
     f.power = a->power[2 + 2 * m], f.frame_max = a->frame_max[2 + 2 * m];
     if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
   }
-  // the kernel queued last is a frontend launch: the emotion stream (which reads none of its outputs) may overlap its tail
-  if (int rc = launch_emotion_stream(a->weights, a->egemaps, a->n_clips, a->expr_sigmoid, stream, /*after_frontend=*/true))
+  // The mouth entries of every output row come from the mel stream (the core) and the expression entries from the emotion
+  // stream alone, so the two kernels do not depend on each other's results: the emotion kernel writes its entries of `out`
+  // itself and the core skips them.  The kernel queued last is a frontend launch; the emotion stream (which reads none of
+  // its outputs) runs on the SMs the frontend's first CTAs leave, the core sets itself up behind both.
+  if (int rc = launch_emotion_stream(a->weights, a->egemaps, a->n_clips, a->expr_sigmoid, a->out, a->sigmoid_out, a->n_out,
+                                     stream, /*after_frontend=*/true))
     return rc;
-  if (int rc = koe_dual_stream_windows(a->weights, a->power, a->frame_max, a->n_edge, a->n_clips, a->n_frames, a->n_out,
-                                       a->stride_frames, a->frames_per_window, a->expr_sigmoid, a->out, a->sigmoid_out,
-                                       a->attn_out, a->precision, stream))
+  if (int rc = launch_dual_stream_windows(a->weights, a->power, a->frame_max, a->n_edge, a->n_clips, a->n_frames, a->n_out,
+                                          a->stride_frames, a->frames_per_window, nullptr, a->out, a->sigmoid_out,
+                                          a->attn_out, a->precision, stream, /*expr_by_emotion_kernel=*/true))
     return rc;
   if (a->smooth && a->n_out > 1)
     if (int rc = koe_ema_scan(a->out, a->n_clips, a->n_out, a->alpha, nullptr, 0, stream)) return rc;

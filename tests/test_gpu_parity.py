@@ -605,3 +605,33 @@ def test_core_standalone_degenerate_shapes(K):
     core.precision = "fp32"
     out = core(torch.zeros(0, 5, 80, device="cuda"), torch.zeros(0, 3, 80, device="cuda"), torch.zeros(0, 256, device="cuda"))
     assert out["blendshapes"].shape == (0, 52)
+
+
+@pytest.mark.parametrize("n_clips", [1, 7, 8, 9, 61, 2049, 2061])
+def test_emotion_stream_clip_counts_vs_oracle(K, n_clips):
+    """koe_emotion_stream over ragged clip counts: a partly filled last CTA, one clip, and the sixteen-clips-per-CTA kernel
+    that large batches take (> 2048 clips); expression sigmoid against the oracle's emotion stream
+    (reference dual_stream_attention.py:234-240)."""
+    import ctypes as C
+    from koemorph_b200 import _lib
+    w = O.make_weights(1237, 30, style="stress")
+    core = K.DualStreamCrossAttention().cuda().eval()
+    core.load_state_dict({k[len("dual_stream_attention."):]: v for k, v in O.model_state_dict(w).items()
+                          if k.startswith("dual_stream_attention.")})
+    rng = np.random.default_rng(n_clips)
+    emo = rng.standard_normal((n_clips, 256)).astype(np.float32)
+    pick = sorted(set([0, n_clips - 1, n_clips // 2, min(n_clips - 1, 2047), min(n_clips - 1, 2048)]))
+    lt = np.full((len(pick), 4, 80), 0.5, np.float32)
+    st = np.full((len(pick), 3, 80), 0.5, np.float32)
+    want = O.dual_stream_core(w, lt, st, emo[pick], return_attention=True)["emotion_blendshapes"]
+    kw = core.kernel_weights()
+    expr = torch.full((n_clips,), float("nan"), device="cuda")
+    e = torch.from_numpy(emo).cuda()
+    _lib.check(_lib.load().koe_emotion_stream(C.byref(kw.struct), e.data_ptr(), n_clips, expr.data_ptr(),
+                                              _lib.stream_ptr(e.device)), "koe_emotion_stream")
+    got = expr.cpu().numpy()
+    assert np.isfinite(got).all()
+    idx = [i for i in range(52) if i not in O.MOUTH_INDICES]
+    for j, c in enumerate(pick):
+        ref = want[j].numpy() if torch.is_tensor(want) else np.asarray(want[j])
+        assert np.abs(ref[idx] - got[c]).max() <= SIG_ATOL, (c, ref[idx][:3], got[c])
