@@ -207,6 +207,7 @@ class ClockSampler:
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
+        self._go = threading.Event()
         self._thread = None
         try:
             import pynvml
@@ -223,6 +224,12 @@ class ClockSampler:
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        # Samples are taken INSIDE the timed region but only once the host has queued all of its steps (release()): an NVML
+        # query holds a driver lock for a millisecond or two, and a kernel launch of the main thread that waits for it
+        # drains the GPU's queue -- 8 us per step of a 20-step region with the sampler polling from the start, 5 us when
+        # it started a millisecond in.  The GPU is still working through the queued steps (the host submits a step in
+        # ~75 us, the GPU runs it in ~200 us) while the clocks and throttle reasons are read.
+        self._go.wait()
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
@@ -239,8 +246,12 @@ class ClockSampler:
             self._thread = threading.Thread(target=self._loop, daemon=True)
             self._thread.start()
 
+    def release(self):
+        self._go.set()
+
     def stop(self):
         self._stop.set()
+        self._go.set()
         if self._thread is not None:
             self._thread.join()
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
@@ -313,13 +324,12 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(tiny)
 
+    sampler = ClockSampler(local)   # (NVML initialisation takes tens of milliseconds: before the warm-up, not between it
+    #                                  and the timed region, where it would leave the GPU idle right before the first step)
     for i in range(max(args.warmup, 3)):
         step(i)
     gather_all()  # warm-up covers the collective too (first use sets up NCCL's channels for this size)
     device_gate()
-    barrier()
-
-    sampler = ClockSampler(local)
     _lib.reset_launch_count()
     barrier()
     sampler.start()
@@ -330,6 +340,7 @@ def run_gpu(args):
     for i in range(K_steps):
         step(i)
     host_submit_ms = (time.perf_counter() - h0) * 1e3
+    sampler.release()
     g0.record()
     gather_all()
     t1.record()
