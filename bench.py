@@ -35,6 +35,28 @@ CONFIG = {"workload": WORKLOAD, "clips_per_step_per_gpu": CLIPS_PER_GPU,
           "l2": "inputs 278.5 MB per GPU > 126 MB L2, no flush needed"}
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+# collective when NCCL_DEBUG asks for it), so the real stdout is set aside at start-up and everything else goes to stderr.
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 # ----------------------------------------------------------------------------- CPU arm: the reference's own forward
 _G = {}
 
@@ -199,7 +221,7 @@ def run_reference(args):
             "gpu_launches": 0}
     if kind == "reference":
         line["cpu_baseline"]["single_process"] = _reference_single_process()
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -330,6 +352,14 @@ def run_gpu(args):
         step(i)
     gather_all()  # warm-up covers the collective too (first use sets up NCCL's channels for this size)
     device_gate()
+    # The ranks reach the first barrier milliseconds apart (process start-up, first-use initialisation), and a GPU that
+    # idles that long answers its next kernels slowly: with one barrier the first timed step of a multi-GPU run took
+    # 406 us instead of 260 us and the next four were still 2-5 % slow (scripts/multi_gpu_step_profile.py).  So the ranks
+    # meet once, run three more untimed steps -- now aligned -- and meet again: that second barrier, the one that brackets
+    # the timed region, is then a matter of microseconds.
+    barrier()
+    for i in range(3):
+        step(i)
     _lib.reset_launch_count()
     barrier()
     sampler.start()
@@ -590,7 +620,7 @@ def run_gpu(args):
             line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -694,6 +724,7 @@ def main():
     ap.add_argument("--no-other-precision", action="store_true", help="skip the secondary (bf16 / fp32) leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the 60 fps / streaming / corpus legs")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
