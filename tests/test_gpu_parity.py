@@ -635,3 +635,33 @@ def test_emotion_stream_clip_counts_vs_oracle(K, n_clips):
     for j, c in enumerate(pick):
         ref = want[j].numpy() if torch.is_tensor(want) else np.asarray(want[j])
         assert np.abs(ref[idx] - got[c]).max() <= SIG_ATOL, (c, ref[idx][:3], got[c])
+
+
+@pytest.mark.parametrize("n_clips", [24, 512])
+def test_back_to_back_forwards_do_not_interfere(K, n_clips):
+    """The forward's kernels are chained with programmatic dependent launch (a kernel's CTAs start while the previous
+    kernel's last CTAs still run) and successive forwards reuse the same workspace addresses: thirty forwards queued
+    without a synchronisation, alternating between two different inputs, must each equal the result of the same forward
+    run alone -- bit for bit, for both cores."""
+    spec = dict(fps=30, wseed=1238, style="stress")
+    m, _ = _model(K, spec, True)
+    g = torch.Generator(device="cuda").manual_seed(n_clips)
+    L = 136000
+    inputs = [(0.1 * torch.randn(n_clips, L, device="cuda", generator=g), torch.randn(n_clips, 264, device="cuda", generator=g))
+              for _ in range(2)]
+    for prec in ("bf16", "fp32"):
+        m.precision = prec
+        alone = []
+        for a, e in inputs:
+            torch.cuda.synchronize()
+            alone.append(m(a, egemaps=e)["blendshapes"].clone())
+            torch.cuda.synchronize()
+        assert not torch.equal(alone[0], alone[1])
+        n = 30 if prec == "bf16" else 6
+        kept = torch.full((n, n_clips, 1, 52), float("nan"), device="cuda")
+        for i in range(n):
+            a, e = inputs[i & 1]
+            m(a, egemaps=e, out=kept[i])
+        torch.cuda.synchronize()
+        for i in range(n):
+            assert torch.equal(kept[i], alone[i & 1]), f"{prec}: forward {i} of the queue differs from the same forward run alone"
