@@ -27,4 +27,4 @@ for rep in range(7):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) / 20)
 ts.sort()
-print(f"step: median {ts[3]*1e3:.1f} us, min {ts[0]*1e3:.1f} us ({os.environ.get('KOE_EMOTION_SIDE') and 'side emotion kernel' or 'default'})")
+print(f"step: median {ts[3]*1e3:.1f} us, min {ts[0]*1e3:.1f} us ({'no programmatic launch' if os.environ.get('KOE_NO_PDL') else 'default'})")
