@@ -56,6 +56,9 @@ inline cudaError_t launch_after_primary_starts(void (*kernel)(KArgs...), dim3 gr
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// frontend launch with launch-chaining knowledge of the caller (csrc/logmel.cu; used by csrc/session.cu)
+int launch_logmel(const koe_frontend_t* fe, const koe_logmel_args* args, void* stream, bool follows_frontend_launch);
+
 #define KOE_REQUIRE(cond, ...)                                   \
   do {                                                           \
     if (!(cond)) return koe::fail(KOE_E_INVALID, __VA_ARGS__);   \

@@ -79,6 +79,7 @@ struct LogmelParams {
   int mid_pairs;                 // interior pairs per clip (0: no edge grouping, every pair is located the slow way)
   int step_clips, step_pairs;    // gridDim.x * kWarps pairs, as whole clips of mid_pairs + a remainder
   int store_order;               // 2 bits per warp class (warp / 4): where its store phase sits (see the kernel)
+  int wait_at_end;               // launch chaining: this launch follows another frontend launch of the same forward (below)
 };
 
 __host__ __device__ constexpr int bitrev5(int i) {
@@ -368,9 +369,18 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
 // kernel to complete first; only THEN are this kernel's own dependents released (the emotion stream, which reads nothing
 // this kernel writes, takes each SM as this kernel's CTA leaves it): a dependent released before the wait could run
 // while the kernel before this one is still reading the buffers that dependent writes.
-__device__ __forceinline__ void pdl_prologue_done() {
-  pdl_wait();
+//
+// `wait_at_end` (the edge-variant launches of a forward, csrc/session.cu): the kernel before this one is another frontend
+// launch of the same forward -- it writes other buffers and has itself waited for everything older -- so this launch
+// neither reads nor writes anything that kernel touches and does not wait for it: its CTAs start on the SMs that kernel's
+// earliest CTAs leave.  It still must not COMPLETE before that kernel has (what follows waits on the last kernel of the
+// chain only), so the wait moves to the end.
+__device__ __forceinline__ void pdl_prologue_done(const LogmelParams& p) {
+  if (!p.wait_at_end) pdl_wait();
   pdl_launch_dependents();
+}
+__device__ __forceinline__ void pdl_epilogue(const LogmelParams& p) {
+  if (p.wait_at_end) pdl_wait();
 }
 
 // ---- the per-pair pieces shared by the two kernel organisations below ------------------------------------------------
@@ -577,7 +587,7 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  pdl_prologue_done();
+  pdl_prologue_done(p);
 
   const unsigned ppc = (unsigned)(p.n_frames + 1) >> 1;  // frame pairs per clip
   const unsigned total_pairs = (unsigned)p.n_clips * ppc;
@@ -651,6 +661,7 @@ logmel_power_kernel(FrontendTables tab, LogmelParams p) {
     bar_wait(mel_done, (k + 1) & 1);
     store_rows(pend_clip, pend_frame, pend_has_b, s_tiles);
   }
+  pdl_epilogue(p);
 }
 
 // ---- warp-specialised organisation (default bank, batch launches) ------------------------------------------------------
@@ -691,7 +702,7 @@ logmel_power_ws_kernel(FrontendTables tab, LogmelParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  pdl_prologue_done();
+  pdl_prologue_done(p);
 
   const unsigned ppc = (unsigned)(p.n_frames + 1) >> 1;
   const unsigned total_pairs = (unsigned)p.n_clips * ppc;
@@ -745,6 +756,7 @@ logmel_power_ws_kernel(FrontendTables tab, LogmelParams p) {
       }
     }
   }
+  pdl_epilogue(p);
 }
 
 constexpr size_t kLogmelWsSmem = sizeof(float) * kFrameLen + sizeof(float2) * 1024 +
@@ -1102,6 +1114,12 @@ extern "C" int koe_debug_k1_variant(int store_order, int warp_specialised) {
 }
 
 extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_args* a, void* stream) {
+  return koe::launch_logmel(fe, a, stream, /*follows_frontend_launch=*/false);
+}
+
+// `follows_frontend_launch`: the kernel queued just before this one on `stream` is another frontend launch of the same
+// forward, writing other buffers (see pdl_prologue_done in the kernels)
+int koe::launch_logmel(const koe_frontend_t* fe, const koe_logmel_args* a, void* stream, bool follows_frontend_launch) {
   KOE_REQUIRE(fe != nullptr && a != nullptr, "koe_logmel_power: NULL argument");
   KOE_REQUIRE(a->n_clips >= 0 && a->n_samples >= 0 && a->n_frames >= 0, "koe_logmel_power: negative size");
   if (a->n_clips == 0 || a->n_frames == 0) return KOE_OK;  // nothing to do: empty buffers may be NULL
@@ -1168,6 +1186,7 @@ extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_ar
   const long long max_grid = (long long)fe->num_sms * fe->occupancy;
   const int grid = (int)std::min(n_blocks, max_grid);
   p.store_order = g_k1_store_order;
+  p.wait_at_end = follows_frontend_launch ? 1 : 0;
   p.mid_pairs = 0, p.step_clips = 0, p.step_pairs = 0;
   if (p.edge_lo + p.edge_hi > 0 && p.edge_lo + p.edge_hi < (int)ppc) {
     p.mid_pairs = (int)ppc - p.edge_lo - p.edge_hi;

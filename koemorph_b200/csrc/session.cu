@@ -151,12 +151,13 @@ extern "C" int koe_forward_windows(const koe_forward_args* a, void* stream) {
     f.n_frames = a->n_out;
     f.frame_step = a->stride_frames;
     f.power_clip_stride = (int64_t)a->n_out * KOE_N_MELS, f.frame_max_clip_stride = a->n_out;
+    // (these launches follow a frontend launch of this forward and touch none of its buffers: they do not wait for it)
     f.frame_offset = m, f.lo_rel_hops = -m, f.hi_rel_hops = KOE_NO_EDGE;
     f.power = a->power[1 + 2 * m], f.frame_max = a->frame_max[1 + 2 * m];
-    if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+    if (int rc = launch_logmel(a->frontend, &f, stream, /*follows_frontend_launch=*/true)) return rc;
     f.frame_offset = a->frames_per_window - 1 - m, f.lo_rel_hops = KOE_NO_EDGE, f.hi_rel_hops = m;
     f.power = a->power[2 + 2 * m], f.frame_max = a->frame_max[2 + 2 * m];
-    if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+    if (int rc = launch_logmel(a->frontend, &f, stream, /*follows_frontend_launch=*/true)) return rc;
   }
   // The mouth entries of every output row come from the mel stream (the core) and the expression entries from the emotion
   // stream alone, so the two kernels do not depend on each other's results: the emotion kernel writes its entries of `out`
