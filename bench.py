@@ -602,7 +602,7 @@ def run_gpu(args):
             "ranks": rank_stats,
             "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "logmel_power_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+            "roofline": {"kernel": "logmel_power_ws_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": k1_ms, "share_of_step": k1_ms / ms_per_step,
                          "algorithmic_bytes_per_launch": k1_bytes,
