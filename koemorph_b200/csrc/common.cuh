@@ -57,7 +57,9 @@ inline cudaError_t launch_after_primary_starts(void (*kernel)(KArgs...), dim3 gr
 }
 
 // frontend launch with launch-chaining knowledge of the caller (csrc/logmel.cu; used by csrc/session.cu)
-int launch_logmel(const koe_frontend_t* fe, const koe_logmel_args* args, void* stream, bool follows_frontend_launch);
+// early_clips / early_flag / early_target: see "early release of the core" in csrc/session.cu (0 / NULL: off)
+int launch_logmel(const koe_frontend_t* fe, const koe_logmel_args* args, void* stream, bool follows_frontend_launch,
+                  int early_clips, unsigned* early_flag, unsigned* early_target);
 
 #define KOE_REQUIRE(cond, ...)                                   \
   do {                                                           \

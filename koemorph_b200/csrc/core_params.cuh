@@ -19,6 +19,12 @@ struct CoreParams {
   int n_long;
   // ring mode (koe_dual_stream_ring): plain and lo-edge rows are slots of per-stream rings, the hi-edge row is per stream
   int ring_frames, ring_base;
+  // early release (csrc/session.cu): items [0, early_items) may be read once *early_flag >= early_target (acquire); the
+  // rest after griddepcontrol.wait.  early_flag == NULL: everything after griddepcontrol.wait, at the start of the kernel.
+  // early_flag[1] counts the CTAs that have finished; the last one clears both words for the next forward.
+  unsigned* early_flag;
+  unsigned early_target;
+  int early_items;
   long long* dbg;  // optional phase timestamps of CTA 0 (bring-up / profiling only), NULL in production
 };
 
@@ -43,6 +49,9 @@ int launch_emotion_stream(const koe_core_weights* w, const float* emo_in, int n_
 int launch_dual_stream_windows(const koe_core_weights* w, const float* const* power, const float* const* frame_max, int n_edge,
                                int n_clips, int n_frames, int n_out, int stride_frames, int frames_per_window,
                                const float* expr_sigmoid, float* out, float* sigmoid_out, float* attn_out, int precision,
-                               void* stream, bool expr_by_emotion_kernel);
+                               void* stream, bool expr_by_emotion_kernel, unsigned* early_flag = nullptr,
+                               unsigned early_target = 0, int early_items = 0, bool* early_applied = nullptr);
+// how many SMs' worth of CTAs the tensor-core core launches for n_items windows (the early-release split follows it)
+int dual_stream_tc_grid(int n_items);
 
 }  // namespace koe

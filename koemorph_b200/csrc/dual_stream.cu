@@ -801,7 +801,9 @@ extern "C" int koe_dual_stream_windows(const koe_core_weights* w, const float* c
 int koe::launch_dual_stream_windows(const koe_core_weights* w, const float* const* power, const float* const* frame_max,
                                     int n_edge, int n_clips, int n_frames, int n_out, int stride_frames,
                                     int frames_per_window, const float* expr_sigmoid, float* out, float* sigmoid_out,
-                                    float* attn_out, int precision, void* stream, bool expr_by_emotion_kernel) {
+                                    float* attn_out, int precision, void* stream, bool expr_by_emotion_kernel,
+                                    unsigned* early_flag, unsigned early_target, int early_items, bool* early_applied) {
+  if (early_applied != nullptr) *early_applied = false;
   if (int rc = validate_weights(w)) return rc;
   if (n_clips == 0 || n_out == 0) return KOE_OK;  // nothing to do: empty buffers may be NULL
   KOE_REQUIRE(power != nullptr && frame_max != nullptr && out != nullptr, "koe_dual_stream_windows: NULL argument");
@@ -836,7 +838,15 @@ int koe::launch_dual_stream_windows(const koe_core_weights* w, const float* cons
   p.out = out;
   p.sigmoid_out = sigmoid_out;
   p.attn_out = attn_out;
-  return launch_core(p, precision, (cudaStream_t)stream);
+  if (early_flag != nullptr && early_target > 0 && early_items > 0 && precision == 2 && n_out == 1 && n_edge == 0 &&
+      attn_out == nullptr && w->k_mel == 259) {
+    p.early_flag = early_flag;
+    p.early_target = early_target;
+    p.early_items = early_items;
+  }
+  const int rc = launch_core(p, precision, (cudaStream_t)stream);
+  if (rc == KOE_OK && early_applied != nullptr) *early_applied = p.early_flag != nullptr;
+  return rc;
 }
 
 extern "C" int koe_dual_stream_ring_edges(const koe_core_weights* w, const float* const* power,

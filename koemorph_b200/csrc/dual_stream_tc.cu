@@ -216,7 +216,10 @@ __device__ __forceinline__ void stamp(long long* dbg, int slot) {
 
 __device__ __forceinline__ void simt_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int KMEL>
+// kEarly: the early-release flavour of the fused forward (see the wait below); a separate instantiation, so that the
+// kernel every other caller runs (streaming, sequences, the public entries) stays exactly as it was: the three extra
+// checks cost that one 4 % through register spills when they were run-time branches
+template <int KMEL, bool kEarly = false>
 __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams p) {
   using G = Geo<KMEL>;
   constexpr int kKMel = G::kKMel, kA1Chunks = G::kA1Chunks, kA1Sbo = G::kA1Sbo, kLongChunks = G::kLongChunks;
@@ -281,8 +284,29 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   const uint32_t tmem = *s_tmem;
   stamp(dk, 1);
   // everything above touched only this CTA's shared memory, TMEM and the weights; the mel rows, frame maxima and
-  // emotion-stream outputs read below come from the previous kernels of the stream
-  pdl_wait();
+  // emotion-stream outputs read below come from the previous kernels of the stream.  Early release (the fused forward,
+  // one window per clip): the frontend's consumer warps count up *early_flag once the rows of the first early_items
+  // clips are stored, which is long before its last CTA has finished -- this kernel's CTAs take SMs as the frontend's
+  // CTAs leave them, and with the flag they start their first windows at once instead of idling until the frontend's
+  // slowest CTA is done.  Acquire: one lane per warp polls, the warp barrier orders the other lanes behind it; the mel-row
+  // producer adds a proxy fence (its reads are TMA copies).  Items from early_items on wait for griddepcontrol.wait.
+  if (kEarly) {
+    if (lane == 0) {
+      unsigned seen = 0;
+      for (uint32_t spin = 0; seen < p.early_target; ++spin) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.early_flag) : "memory");
+        if (seen < p.early_target) {
+          __nanosleep(64);
+          if (spin > (1u << 22)) __trap();
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    pdl_wait();
+  }
+  // (early_items is a multiple of the grid: a CTA's first item that the flag does not cover is early_items + blockIdx.x)
+  const int first_late_item = kEarly ? p.early_items + (int)blockIdx.x : 0;
   // (no griddepcontrol.launch_dependents here: released early, the next forward's frontend CTAs take the SMs that this
   // kernel's last partial round of windows leaves idle and the step gets 11 us SLOWER -- measured, 198.6 vs 209.5 us)
 
@@ -328,6 +352,10 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         long long* dp = (p.dbg != nullptr && blockIdx.x == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 32 + 16 * (item / gridDim.x) : nullptr;
         const int b = item / p.n_out, wi = item % p.n_out;
+        if (kEarly) {
+          if (item == first_late_item) pdl_wait();
+          asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy acquire above -> TMA reads below
+        }
         const float* base = p.ring_frames > 0 ? p.power[0] + (size_t)b * p.ring_frames * kTok
                                               : p.power[0] + window_row(p, 0, b, wi, 0) * kTok;
         // Ring mode (the streaming step): with thousands of streams the rings (82 KB each: 335 MB for 4096 streams) do not
@@ -519,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
             const int k = T >= 3 ? T - 3 + e : (e < T ? e : -1);
             if (k >= 0) {
               const int var = window_variant(p, k);
-              extra[e] = __ldg(p.power[var] + window_row(p, var, b, wi, k) * kTok + tid);
+              extra[e] = p.power[var][window_row(p, var, b, wi, k) * kTok + tid];
             } else {
               extra[e] = -INFINITY;
             }
@@ -664,6 +692,8 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
         mbar_arrive(bar_go);
       }
       stamp(ds, 1);
+      // (early release: the next window is this CTA's first whose clip the flag does not cover -- it is read from here on)
+      if (kEarly && has_next && item + (int)gridDim.x == first_late_item) pdl_wait();
       const float mx_next = kStageAhead && has_next ? frame_max_partial(item + gridDim.x) : -INFINITY;
 
       // ---- E1: bias + LayerNorm of token row tid -> enc (bf16, K-major) -------------------------------
@@ -857,6 +887,15 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
   }
+  if (kEarly) {
+    // this kernel must not complete before the kernels ahead of it have (what follows waits on this kernel only); the
+    // last CTA out clears the flag and the exit counter for the next forward on this stream
+    pdl_wait();
+    if (tid == 0 && atomicAdd(p.early_flag + 1, 1u) == gridDim.x - 1) {
+      p.early_flag[0] = 0;
+      p.early_flag[1] = 0;
+    }
+  }
   if (p.dbg != nullptr && tid == 0) {
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
@@ -865,6 +904,14 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
 }
 
 }  // namespace tc
+
+int dual_stream_tc_grid(int n_items) {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (sms[dev] == 0 && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return std::min(n_items, sms[dev]);
+}
 
 int launch_dual_stream_tc(const CoreParams& p, int precision, cudaStream_t stream) {
   if (precision != 2)
@@ -892,7 +939,18 @@ int launch_dual_stream_tc(const CoreParams& p, int precision, cudaStream_t strea
     KOE_CUDA(cudaMemsetAsync(p.attn_out, 0, (size_t)p.n_clips * p.n_out * KOE_N_MOUTH * tc::kTok * sizeof(float),
                              stream));
   const int grid = std::min(p.n_clips * p.n_out, num_sms[dev]);
-  if (p.w.k_mel == 259)
+  if (p.early_flag != nullptr) {
+    KOE_REQUIRE(p.w.k_mel == 259 && p.n_out == 1 && p.early_items > 0 && p.early_items % grid == 0 && p.early_target > 0,
+                "tensor-core path: bad early-release parameters");
+    static bool configured[64] = {false};
+    if (!configured[dev]) {
+      KOE_CUDA(cudaFuncSetAttribute(tc::dual_stream_tc_kernel<259, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    tc::kSmemBytes));
+      configured[dev] = true;
+    }
+    KOE_CUDA(launch_after_primary_starts(tc::dual_stream_tc_kernel<259, true>, dim3(grid), dim3(tc::kThreads), tc::kSmemBytes,
+                                         stream, p));
+  } else if (p.w.k_mel == 259)
     KOE_CUDA(launch_after_primary_starts(tc::dual_stream_tc_kernel<259>, dim3(grid), dim3(tc::kThreads), tc::kSmemBytes, stream, p));
   else
     KOE_CUDA(launch_after_primary_starts(tc::dual_stream_tc_kernel<515>, dim3(grid), dim3(tc::kThreads), tc::kSmemBytes, stream, p));

@@ -80,6 +80,10 @@ struct LogmelParams {
   int step_clips, step_pairs;    // gridDim.x * kWarps pairs, as whole clips of mid_pairs + a remainder
   int store_order;               // 2 bits per warp class (warp / 4): where its store phase sits (see the kernel)
   int wait_at_end;               // launch chaining: this launch follows another frontend launch of the same forward (below)
+  // early release of the core (csrc/session.cu): every consumer warp adds one to *early_flag (release) when its CTA has
+  // stored the rows of all its iterations below early_iters -- the core's first rounds of windows need no more than that
+  unsigned* early_flag;
+  unsigned early_iters;
 };
 
 __host__ __device__ constexpr int bitrev5(int i) {
@@ -754,6 +758,18 @@ logmel_power_ws_kernel(FrontendTables tab, LogmelParams p) {
         const int4 pi = s_pair[(k & 1) * kWarps + w];
         if (pi.y >= 0) store_pair_rows<false>(tab, p, pi.x, pi.y, pi.z != 0, tiles, 2 * w, lane);
       }
+      if (p.early_flag != nullptr) {
+        // this CTA's last iteration below the threshold: its rows (this warp's share, and in program order all earlier
+        // ones) are stored -> release them to the core, which acquires the counter (8 arrivals per CTA)
+        const unsigned it = first + k * stride;
+        if (it < p.early_iters && it + stride >= p.early_iters) {
+          __syncwarp();
+          if (lane == 0) {
+            __threadfence();
+            atomicAdd(p.early_flag, 1u);
+          }
+        }
+      }
     }
   }
   pdl_epilogue(p);
@@ -1114,12 +1130,13 @@ extern "C" int koe_debug_k1_variant(int store_order, int warp_specialised) {
 }
 
 extern "C" int koe_logmel_power_ex(const koe_frontend_t* fe, const koe_logmel_args* a, void* stream) {
-  return koe::launch_logmel(fe, a, stream, /*follows_frontend_launch=*/false);
+  return koe::launch_logmel(fe, a, stream, /*follows_frontend_launch=*/false, 0, nullptr, nullptr);
 }
 
 // `follows_frontend_launch`: the kernel queued just before this one on `stream` is another frontend launch of the same
 // forward, writing other buffers (see pdl_prologue_done in the kernels)
-int koe::launch_logmel(const koe_frontend_t* fe, const koe_logmel_args* a, void* stream, bool follows_frontend_launch) {
+int koe::launch_logmel(const koe_frontend_t* fe, const koe_logmel_args* a, void* stream, bool follows_frontend_launch,
+                       int early_clips, unsigned* early_flag, unsigned* early_target) {
   KOE_REQUIRE(fe != nullptr && a != nullptr, "koe_logmel_power: NULL argument");
   KOE_REQUIRE(a->n_clips >= 0 && a->n_samples >= 0 && a->n_frames >= 0, "koe_logmel_power: negative size");
   if (a->n_clips == 0 || a->n_frames == 0) return KOE_OK;  // nothing to do: empty buffers may be NULL
@@ -1187,12 +1204,29 @@ int koe::launch_logmel(const koe_frontend_t* fe, const koe_logmel_args* a, void*
   const int grid = (int)std::min(n_blocks, max_grid);
   p.store_order = g_k1_store_order;
   p.wait_at_end = follows_frontend_launch ? 1 : 0;
+  p.early_flag = nullptr, p.early_iters = 0;
   p.mid_pairs = 0, p.step_clips = 0, p.step_pairs = 0;
   if (p.edge_lo + p.edge_hi > 0 && p.edge_lo + p.edge_hi < (int)ppc) {
     p.mid_pairs = (int)ppc - p.edge_lo - p.edge_hi;
     const long long step = (long long)grid * kWarps;
     p.step_clips = (int)(step / p.mid_pairs);
     p.step_pairs = (int)(step % p.mid_pairs);
+  }
+  // Early release of the core: the clips [0, early_clips) are complete once every pair ahead of clip `early_clips` in the
+  // launch order is stored -- all edge pairs (they come first) and the interior pairs of those clips -- i.e. once every
+  // CTA has finished its iterations below early_iters.  Only the warp-specialised kernel signals; every CTA must own an
+  // iteration below the threshold and one at or above it.
+  if (early_target != nullptr) *early_target = 0;
+  if (early_flag != nullptr && early_clips > 0 && early_clips < a->n_clips && p.power_b == nullptr && fe->default_bank &&
+      g_k1_warp_specialised == 1) {
+    const long long before = p.mid_pairs > 0 ? (long long)a->n_clips * (p.edge_lo + p.edge_hi) + (long long)early_clips * p.mid_pairs
+                                             : (long long)early_clips * ppc;
+    const long long iters = (before + kWarps - 1) / kWarps;
+    if (iters >= grid && iters + grid <= n_blocks) {
+      p.early_flag = early_flag;
+      p.early_iters = (unsigned)iters;
+      *early_target = (unsigned)grid * 8u;  // consumer warps per CTA (logmel_power_ws_kernel<8, ...>)
+    }
   }
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t le;

@@ -9,6 +9,10 @@
 // mel rows with their per-frame maxima, one "window ends here" row (L), the smoothing state.  SURVEY.md section 8
 // note E: frame n is centred on sample n * hop; R[n] is the same frame with everything before its centre zeroed; L[n + 1]
 // is centred on (n + 1) * hop with everything from there on zeroed.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "core_params.cuh"
 
 namespace koe {
@@ -118,6 +122,40 @@ extern "C" int koe_stream_push(const koe_stream_args* a, int* emitted, void* str
   return KOE_OK;
 }
 
+// ---- early release of the core ------------------------------------------------------------------------------------------
+// With one window per clip the core's CTA b handles clips b, b + G, b + 2G, ... (G = its grid).  The frontend stores the
+// clips in index order, so all but the last round of windows can be read long before the frontend's slowest CTA has
+// finished -- and the core's CTAs become resident exactly then, as the frontend's first CTAs leave.  The frontend's
+// consumer warps count up a flag when the first E = G * floor((n - 1) / G) clips are stored; the core acquires it instead
+// of waiting for the whole frontend, and executes griddepcontrol.wait only before its last round (step 199.1 -> 191.9 us
+// at most, measured with a probe that did not wait at all).  The flag and the core's exit counter live in two words per
+// (device, stream), zero between forwards: the last core CTA out clears them.
+namespace {
+struct EarlyFlags {
+  std::mutex mu;
+  std::map<std::pair<int, void*>, unsigned*> words;
+  unsigned* get(void* stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = words.find({dev, stream});
+    if (it != words.end()) return it->second;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+      return nullptr;   // (no allocation inside a capture: that forward takes the plain chain)
+    unsigned* w = nullptr;
+    if (cudaMalloc(&w, 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
+    if (cudaMemset(w, 0, 2 * sizeof(unsigned)) != cudaSuccess) {
+      cudaFree(w);
+      return nullptr;
+    }
+    words[{dev, stream}] = w;
+    return w;
+  }
+};
+EarlyFlags g_early;
+}  // namespace
+
 // ---- the batch forward as one native call (see koe_forward_windows in the header) ------------------------------------
 extern "C" int koe_forward_windows(const koe_forward_args* a, void* stream) {
   KOE_REQUIRE(a != nullptr && a->frontend != nullptr && a->weights != nullptr, "koe_forward_windows: NULL argument");
@@ -143,7 +181,23 @@ extern "C" int koe_forward_windows(const koe_forward_args* a, void* stream) {
   f.lo_rel_hops = KOE_NO_EDGE, f.hi_rel_hops = KOE_NO_EDGE;
   f.power = a->power[0], f.power_clip_stride = (int64_t)a->n_frames * KOE_N_MELS;
   f.frame_max = a->frame_max[0], f.frame_max_clip_stride = a->n_frames;
-  if (int rc = koe_logmel_power_ex(a->frontend, &f, stream)) return rc;
+  // early release of the core (above): one window per clip, tensor-core core, no attention output, more than one round
+  static const bool early_off = getenv("KOE_NO_EARLY_CORE") != nullptr;  // experiment switch
+  unsigned* early_flag = nullptr;
+  unsigned early_target = 0;
+  int early_clips = 0;
+  if (!early_off && a->n_out == 1 && a->n_edge == 0 && a->precision == 2 && a->attn_out == nullptr &&
+      a->weights->k_mel == 259) {
+    const int G = dual_stream_tc_grid(a->n_clips);
+    if (G > 0 && a->n_clips > G) {
+      early_clips = G * ((a->n_clips - 1) / G);
+      early_flag = g_early.get(stream);
+    }
+  }
+  if (int rc = launch_logmel(a->frontend, &f, stream, /*follows_frontend_launch=*/false, early_clips, early_flag, &early_target))
+    return rc;
+  if (early_target == 0) early_flag = nullptr;
+  bool early_applied = false;
   // the frames within n_fft/2 of a window edge, once per window (SURVEY.md section 8 note E)
   for (int m = 0; m < a->n_edge; ++m) {
     KOE_REQUIRE(a->power[1 + 2 * m] && a->power[2 + 2 * m] && a->frame_max[1 + 2 * m] && a->frame_max[2 + 2 * m],
@@ -154,22 +208,29 @@ extern "C" int koe_forward_windows(const koe_forward_args* a, void* stream) {
     // (these launches follow a frontend launch of this forward and touch none of its buffers: they do not wait for it)
     f.frame_offset = m, f.lo_rel_hops = -m, f.hi_rel_hops = KOE_NO_EDGE;
     f.power = a->power[1 + 2 * m], f.frame_max = a->frame_max[1 + 2 * m];
-    if (int rc = launch_logmel(a->frontend, &f, stream, /*follows_frontend_launch=*/true)) return rc;
+    if (int rc = launch_logmel(a->frontend, &f, stream, /*follows_frontend_launch=*/true, 0, nullptr, nullptr)) return rc;
     f.frame_offset = a->frames_per_window - 1 - m, f.lo_rel_hops = KOE_NO_EDGE, f.hi_rel_hops = m;
     f.power = a->power[2 + 2 * m], f.frame_max = a->frame_max[2 + 2 * m];
-    if (int rc = launch_logmel(a->frontend, &f, stream, /*follows_frontend_launch=*/true)) return rc;
+    if (int rc = launch_logmel(a->frontend, &f, stream, /*follows_frontend_launch=*/true, 0, nullptr, nullptr)) return rc;
   }
   // The mouth entries of every output row come from the mel stream (the core) and the expression entries from the emotion
   // stream alone, so the two kernels do not depend on each other's results: the emotion kernel writes its entries of `out`
   // itself and the core skips them.  The kernel queued last is a frontend launch; the emotion stream (which reads none of
   // its outputs) runs on the SMs the frontend's first CTAs leave, the core sets itself up behind both.
   if (int rc = launch_emotion_stream(a->weights, a->egemaps, a->n_clips, a->expr_sigmoid, a->out, a->sigmoid_out, a->n_out,
-                                     stream, /*after_frontend=*/true))
+                                     stream, /*after_frontend=*/true)) {
+    if (early_flag != nullptr) cudaMemsetAsync(early_flag, 0, 2 * sizeof(unsigned), (cudaStream_t)stream);
     return rc;
+  }
   if (int rc = launch_dual_stream_windows(a->weights, a->power, a->frame_max, a->n_edge, a->n_clips, a->n_frames, a->n_out,
                                           a->stride_frames, a->frames_per_window, nullptr, a->out, a->sigmoid_out,
-                                          a->attn_out, a->precision, stream, /*expr_by_emotion_kernel=*/true))
+                                          a->attn_out, a->precision, stream, /*expr_by_emotion_kernel=*/true, early_flag,
+                                          early_target, early_clips, &early_applied)) {
+    if (early_flag != nullptr) cudaMemsetAsync(early_flag, 0, 2 * sizeof(unsigned), (cudaStream_t)stream);  // frontend counted, nobody clears
     return rc;
+  }
+  // (the frontend counted but the core took the plain kernel: the flag must not survive this forward)
+  if (early_flag != nullptr && !early_applied) KOE_CUDA(cudaMemsetAsync(early_flag, 0, 2 * sizeof(unsigned), (cudaStream_t)stream));
   if (a->smooth && a->n_out > 1)
     if (int rc = koe_ema_scan(a->out, a->n_clips, a->n_out, a->alpha, nullptr, 0, stream)) return rc;
   return KOE_OK;

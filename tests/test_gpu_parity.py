@@ -665,3 +665,24 @@ def test_back_to_back_forwards_do_not_interfere(K, n_clips):
         torch.cuda.synchronize()
         for i in range(n):
             assert torch.equal(kept[i], alone[i & 1]), f"{prec}: forward {i} of the queue differs from the same forward run alone"
+
+
+@pytest.mark.parametrize("n_clips", [149, 297, 445, 512, 700])
+def test_early_released_core_equals_the_plain_chain(K, n_clips):
+    """Batches of more than one round of windows take the early-release chain (the core starts its first rounds on a flag
+    of the frontend instead of waiting for the whole frontend, csrc/session.cu).  Its result must equal, bit for bit, the
+    same kernels issued one by one through the public entries (plain stream order, no flag), on repeated calls."""
+    spec = dict(fps=30, wseed=1239, style="stress")
+    m, _ = _model(K, spec, True)
+    m.precision = "bf16"
+    g = torch.Generator(device="cuda").manual_seed(n_clips)
+    audio = 0.1 * torch.randn(n_clips, 136000, device="cuda", generator=g)
+    audio[::7] *= 1e-3                                    # quiet clips: a stale (zero / garbage) row would move their dB reference
+    eg = torch.randn(n_clips, 264, device="cuda", generator=g)
+    fe = m._frontend(audio.device)
+    power, fmax = fe.power(audio, 533, 257)
+    want, _, _ = m._core_windows([power], [fmax], 0, n_clips, 257, 1, 1, 257, m._check_egemaps(eg, n_clips, audio.device), False)
+    torch.cuda.synchronize()
+    for rep in range(4):
+        got = m(audio, egemaps=eg)["blendshapes"]
+        assert torch.equal(got.reshape(want.shape), want), f"call {rep}: early-released forward differs from the plain chain"
