@@ -132,23 +132,31 @@ extern "C" int koe_stream_push(const koe_stream_args* a, int* emitted, void* str
 // (device, stream), zero between forwards: the last core CTA out clears them.
 namespace {
 struct EarlyFlags {
+  static constexpr int kPool = 64;   // word pairs per device, allocated (and zeroed) at the first use outside a capture
   std::mutex mu;
   std::map<std::pair<int, void*>, unsigned*> words;
+  std::map<int, std::pair<unsigned*, int>> pool;   // device -> (block, pairs handed out)
   unsigned* get(void* stream) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     std::lock_guard<std::mutex> lock(mu);
     auto it = words.find({dev, stream});
     if (it != words.end()) return it->second;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
-      return nullptr;   // (no allocation inside a capture: that forward takes the plain chain)
-    unsigned* w = nullptr;
-    if (cudaMalloc(&w, 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
-    if (cudaMemset(w, 0, 2 * sizeof(unsigned)) != cudaSuccess) {
-      cudaFree(w);
-      return nullptr;
+    auto pl = pool.find(dev);
+    if (pl == pool.end()) {
+      // (no allocation inside a stream capture: a forward captured before any eager one takes the plain chain)
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
+      unsigned* block = nullptr;
+      if (cudaMalloc(&block, kPool * 2 * sizeof(unsigned)) != cudaSuccess) return nullptr;
+      if (cudaMemset(block, 0, kPool * 2 * sizeof(unsigned)) != cudaSuccess) {
+        cudaFree(block);
+        return nullptr;
+      }
+      pl = pool.emplace(dev, std::make_pair(block, 0)).first;
     }
+    if (pl->second.second >= kPool) return nullptr;   // more streams than pairs: those forwards take the plain chain
+    unsigned* w = pl->second.first + 2 * pl->second.second++;
     words[{dev, stream}] = w;
     return w;
   }
