@@ -32,3 +32,9 @@ print("core CTAs    start:", pct(core[:, 0]), "  end:", pct(core[:, 1]), "(us af
 print("emotion CTAs start:", pct(emo[:, 0]))
 print("             work done:", pct(emo[:, 1]), "  left:", pct(emo[:, 2]))
 print("emotion CTA work time (us): min %.1f median %.1f max %.1f" % tuple(np.percentile((emo[:, 1] - emo[:, 0]) / 1e3, [0, 50, 100])))
+n4 = B % 148 if B % 148 else 148
+for name, sl in (("CTAs with one window more (blockIdx < %d)" % n4, slice(0, n4)), ("the others", slice(n4, 148))):
+    if core[sl].size:
+        print("%-46s start: %s   end: %s" % (name, pct(core[sl, 0]), pct(core[sl, 1])))
+order = np.argsort(core[:, 0])
+print("blockIdx of the first 12 core CTAs to start:", order[:12].tolist(), " of the last 12:", order[-12:].tolist())
