@@ -686,3 +686,30 @@ def test_early_released_core_equals_the_plain_chain(K, n_clips):
     for rep in range(4):
         got = m(audio, egemaps=eg)["blendshapes"]
         assert torch.equal(got.reshape(want.shape), want), f"call {rep}: early-released forward differs from the plain chain"
+
+
+def test_early_released_core_in_a_replayed_cuda_graph(K):
+    """Three forwards of a batch that takes the early-release chain, captured in one CUDA graph: every replay must leave
+    the release flag cleared for the next one (the last core CTA out clears it) and reproduce the eager results bit for
+    bit, also interleaved with eager calls on the same stream."""
+    spec = dict(fps=30, wseed=1240, style="stress")
+    m, _ = _model(K, spec, True)
+    m.precision = "bf16"
+    n = 300
+    g = torch.Generator(device="cuda").manual_seed(9)
+    audio = 0.1 * torch.randn(n, 136000, device="cuda", generator=g)
+    eg = torch.randn(n, 264, device="cuda", generator=g)
+    want = m(audio, egemaps=eg)["blendshapes"].clone()     # eager (allocates the flag words outside any capture)
+    outs = torch.zeros(3, n, 1, 52, device="cuda")
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(3):
+            m(audio, egemaps=eg, out=outs[i])
+    for rep in range(4):
+        outs.zero_()
+        graph.replay()
+        if rep % 2:
+            assert torch.equal(m(audio, egemaps=eg)["blendshapes"], want)   # an eager forward between replays
+        torch.cuda.synchronize()
+        for i in range(3):
+            assert torch.equal(outs[i], want), f"replay {rep}, forward {i}"
