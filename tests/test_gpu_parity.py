@@ -713,3 +713,30 @@ def test_early_released_core_in_a_replayed_cuda_graph(K):
         torch.cuda.synchronize()
         for i in range(3):
             assert torch.equal(outs[i], want), f"replay {rep}, forward {i}"
+
+
+def test_early_released_core_on_two_streams(K):
+    """Forwards that take the early-release chain, queued on two streams at once (each stream has its own flag words):
+    results equal the same forwards run alone."""
+    spec = dict(fps=30, wseed=1241, style="stress")
+    m, _ = _model(K, spec, True)
+    m.precision = "bf16"
+    n = 300
+    g = torch.Generator(device="cuda").manual_seed(10)
+    ins = [(0.1 * torch.randn(n, 136000, device="cuda", generator=g), torch.randn(n, 264, device="cuda", generator=g)) for _ in range(2)]
+    want = [m(a, egemaps=e)["blendshapes"].clone() for a, e in ins]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = torch.zeros(2, 4, n, 1, 52, device="cuda")
+    for s in streams:
+        s.wait_stream(torch.cuda.current_stream())
+    for i in range(4):
+        for k, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                m._forward_frames(ins[k][0], m._check_egemaps(ins[k][1], n, ins[k][0].device), False, out=outs[k, i])
+    for s in streams:
+        torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    for k in range(2):
+        for i in range(4):
+            assert torch.equal(outs[k, i], want[k]), f"stream {k}, forward {i}"
