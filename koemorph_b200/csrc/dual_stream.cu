@@ -839,7 +839,7 @@ int koe::launch_dual_stream_windows(const koe_core_weights* w, const float* cons
   p.sigmoid_out = sigmoid_out;
   p.attn_out = attn_out;
   if (early_flag != nullptr && early_target > 0 && early_items > 0 && precision == 2 && n_out == 1 && n_edge == 0 &&
-      attn_out == nullptr && w->k_mel == 259) {
+      attn_out == nullptr && (w->k_mel == 259 || w->k_mel == 515)) {
     p.early_flag = early_flag;
     p.early_target = early_target;
     p.early_items = early_items;

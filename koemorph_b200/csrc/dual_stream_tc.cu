@@ -687,6 +687,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       long long* ds = (p.dbg != nullptr && blockIdx.x == 0 && tid == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 16 * (item / gridDim.x) : nullptr;
       stamp(ds, 0);
       if (!kStageAhead) {
+        if (kEarly && item == first_late_item) pdl_wait();  // (early release: this window's clip is not covered by the flag)
         stage_window(item, frame_max_partial(item), ds);
         fence_async_smem();
         mbar_arrive(bar_go);
@@ -940,16 +941,22 @@ int launch_dual_stream_tc(const CoreParams& p, int precision, cudaStream_t strea
                              stream));
   const int grid = std::min(p.n_clips * p.n_out, num_sms[dev]);
   if (p.early_flag != nullptr) {
-    KOE_REQUIRE(p.w.k_mel == 259 && p.n_out == 1 && p.early_items > 0 && p.early_items % grid == 0 && p.early_target > 0,
+    KOE_REQUIRE(p.n_out == 1 && p.early_items > 0 && p.early_items % grid == 0 && p.early_target > 0,
                 "tensor-core path: bad early-release parameters");
     static bool configured[64] = {false};
     if (!configured[dev]) {
       KOE_CUDA(cudaFuncSetAttribute(tc::dual_stream_tc_kernel<259, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     tc::kSmemBytes));
+      KOE_CUDA(cudaFuncSetAttribute(tc::dual_stream_tc_kernel<515, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    tc::kSmemBytes));
       configured[dev] = true;
     }
-    KOE_CUDA(launch_after_primary_starts(tc::dual_stream_tc_kernel<259, true>, dim3(grid), dim3(tc::kThreads), tc::kSmemBytes,
-                                         stream, p));
+    if (p.w.k_mel == 259)
+      KOE_CUDA(launch_after_primary_starts(tc::dual_stream_tc_kernel<259, true>, dim3(grid), dim3(tc::kThreads), tc::kSmemBytes,
+                                           stream, p));
+    else
+      KOE_CUDA(launch_after_primary_starts(tc::dual_stream_tc_kernel<515, true>, dim3(grid), dim3(tc::kThreads), tc::kSmemBytes,
+                                           stream, p));
   } else if (p.w.k_mel == 259)
     KOE_CUDA(launch_after_primary_starts(tc::dual_stream_tc_kernel<259>, dim3(grid), dim3(tc::kThreads), tc::kSmemBytes, stream, p));
   else

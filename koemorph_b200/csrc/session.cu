@@ -195,7 +195,7 @@ extern "C" int koe_forward_windows(const koe_forward_args* a, void* stream) {
   unsigned early_target = 0;
   int early_clips = 0;
   if (!early_off && a->n_out == 1 && a->n_edge == 0 && a->precision == 2 && a->attn_out == nullptr &&
-      a->weights->k_mel == 259) {
+      (a->weights->k_mel == 259 || a->weights->k_mel == 515)) {
     const int G = dual_stream_tc_grid(a->n_clips);
     if (G > 0 && a->n_clips > G) {
       early_clips = G * ((a->n_clips - 1) / G);

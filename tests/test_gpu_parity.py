@@ -667,21 +667,22 @@ def test_back_to_back_forwards_do_not_interfere(K, n_clips):
             assert torch.equal(kept[i], alone[i & 1]), f"{prec}: forward {i} of the queue differs from the same forward run alone"
 
 
-@pytest.mark.parametrize("n_clips", [149, 297, 445, 512, 700])
-def test_early_released_core_equals_the_plain_chain(K, n_clips):
+@pytest.mark.parametrize("fps,n_clips", [(30, 149), (30, 297), (30, 445), (30, 512), (30, 700), (60, 300), (60, 512)])
+def test_early_released_core_equals_the_plain_chain(K, fps, n_clips):
     """Batches of more than one round of windows take the early-release chain (the core starts its first rounds on a flag
     of the frontend instead of waiting for the whole frontend, csrc/session.cu).  Its result must equal, bit for bit, the
     same kernels issued one by one through the public entries (plain stream order, no flag), on repeated calls."""
-    spec = dict(fps=30, wseed=1239, style="stress")
+    spec = dict(fps=fps, wseed=1239, style="stress")
     m, _ = _model(K, spec, True)
     m.precision = "bf16"
+    hop, T = m.hop_length, m.window_frames + 1
     g = torch.Generator(device="cuda").manual_seed(n_clips)
     audio = 0.1 * torch.randn(n_clips, 136000, device="cuda", generator=g)
     audio[::7] *= 1e-3                                    # quiet clips: a stale (zero / garbage) row would move their dB reference
     eg = torch.randn(n_clips, 264, device="cuda", generator=g)
     fe = m._frontend(audio.device)
-    power, fmax = fe.power(audio, 533, 257)
-    want, _, _ = m._core_windows([power], [fmax], 0, n_clips, 257, 1, 1, 257, m._check_egemaps(eg, n_clips, audio.device), False)
+    power, fmax = fe.power(audio, hop, T)
+    want, _, _ = m._core_windows([power], [fmax], 0, n_clips, T, 1, 1, T, m._check_egemaps(eg, n_clips, audio.device), False)
     torch.cuda.synchronize()
     for rep in range(4):
         got = m(audio, egemaps=eg)["blendshapes"]
