@@ -313,7 +313,11 @@ int koe_stream_push(const koe_stream_args* args, int* emitted, void* stream);
  * single-kernel entries above keep plain stream order.  The expression entries of `out` depend on the emotion stream only
  * and the mouth entries on the mel stream only, so here the emotion kernel writes its 24 entries of every output row
  * itself (and expr_sigmoid, as koe_emotion_stream would) and the core leaves them alone: neither waits for the other's
- * results.  Window i of a clip starts at global frame i * stride_frames and holds
+ * results.  With one window per clip (n_out = 1, n_edge = 0, precision 2, no attention output) and more clips than SMs,
+ * the core does not wait for the whole frontend either: it starts every round of windows but its last on a release /
+ * acquire flag that the frontend counts up once those clips are stored (two words per device and stream, owned by the
+ * library, zero between calls).  Results are identical to the kernels run one after the other.
+ * Window i of a clip starts at global frame i * stride_frames and holds
  * frames_per_window frames; n_frames >= (n_out - 1) * stride_frames + frames_per_window global frames are computed.
  * Workspace (caller-owned): power[0] / frame_max[0] [n_clips][n_frames][80] / [n_clips][n_frames]; for m < n_edge
  * power[1 + 2m], power[2 + 2m] [n_clips][n_out][80] (+ frame_max); expr_sigmoid [n_clips].
