@@ -667,7 +667,7 @@ def test_back_to_back_forwards_do_not_interfere(K, n_clips):
             assert torch.equal(kept[i], alone[i & 1]), f"{prec}: forward {i} of the queue differs from the same forward run alone"
 
 
-@pytest.mark.parametrize("fps,n_clips", [(30, 149), (30, 297), (30, 445), (30, 512), (30, 700), (60, 300), (60, 512)])
+@pytest.mark.parametrize("fps,n_clips", [(30, 149), (30, 297), (30, 445), (30, 512), (30, 700), (30, 2100), (60, 300), (60, 512)])
 def test_early_released_core_equals_the_plain_chain(K, fps, n_clips):
     """Batches of more than one round of windows take the early-release chain (the core starts its first rounds on a flag
     of the frontend instead of waiting for the whole frontend, csrc/session.cu).  Its result must equal, bit for bit, the
