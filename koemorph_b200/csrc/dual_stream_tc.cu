@@ -229,6 +229,9 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const koe_core_weights& W = p.w;
+  // early release: a first look at the flag now, so that its L2 round trip runs beside the prologue (used below)
+  unsigned early_seen = 0;
+  if (kEarly && lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(early_seen) : "l"(p.early_flag) : "memory");
   long long* dk = (p.dbg != nullptr && blockIdx.x == 0 && tid == 0) ? p.dbg + 120 : nullptr;
   stamp(dk, 0);
   if (p.dbg != nullptr && tid == 0) {  // per-CTA wall-clock span (ns) for the launch-level picture
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
   // producer adds a proxy fence (its reads are TMA copies).  Items from early_items on wait for griddepcontrol.wait.
   if (kEarly) {
     if (lane == 0) {
-      unsigned seen = 0;
+      unsigned seen = early_seen;
       for (uint32_t spin = 0; seen < p.early_target; ++spin) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.early_flag) : "memory");
         if (seen < p.early_target) {
@@ -352,9 +355,9 @@ __global__ void __launch_bounds__(kThreads, 1) dual_stream_tc_kernel(CoreParams 
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         long long* dp = (p.dbg != nullptr && blockIdx.x == 0 && item < 2 * (int)gridDim.x) ? p.dbg + 32 + 16 * (item / gridDim.x) : nullptr;
         const int b = item / p.n_out, wi = item % p.n_out;
-        if (kEarly) {
+        if (kEarly && (item == (int)blockIdx.x || item == first_late_item)) {
           if (item == first_late_item) pdl_wait();
-          asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy acquire above -> TMA reads below
+          asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy acquire / wait above -> TMA reads below
         }
         const float* base = p.ring_frames > 0 ? p.power[0] + (size_t)b * p.ring_frames * kTok
                                               : p.power[0] + window_row(p, 0, b, wi, 0) * kTok;
